@@ -1,0 +1,78 @@
+// demcz_internal.h — context layout and internal entry points shared by the library's
+// translation units (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+#include "../../include/demcz.h"
+
+enum { DEMCZ_LIK_NONE = -1, DEMCZ_LIK_MVN = 0, DEMCZ_LIK_LINREG = 1 };
+
+struct demcz_linreg_state;   // demcz_linreg.cu
+
+struct demcz_ctx {
+    demcz_opts o{};
+    std::vector<int32_t> block_ptr, block_idx;
+    std::vector<double> eps;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    int LD = 0;          // archive row stride in floats (d rounded up to 4 -> 16-byte aligned rows)
+    int ldx = 0;         // SoA leading dimension (N rounded up to 32)
+    int stages = 2;
+
+    int lik_kind = DEMCZ_LIK_NONE;
+    std::vector<float> mvn_mu, mvn_W;   // W = L^-1, row-major d x d (lower)
+    float mvn_c0 = 0.f;
+    demcz_linreg_state* linreg = nullptr;
+
+    // device state
+    float* dX = nullptr;        // [d][ldx]
+    float* dlogp = nullptr;     // [ldx]
+    float* dZ = nullptr;        // [zcap][LD]
+    int64_t zcap = 0;
+    int64_t M = 0;              // rows appended so far (valid rows = min(M, zcap))
+    float* dT = nullptr;        // temperature table
+    float* dhist = nullptr;     // [G][d][N]
+    float* dlphist = nullptr;   // [G][N]
+    uint32_t* tr_r1 = nullptr; uint32_t* tr_r2 = nullptr; float* tr_u = nullptr; float* tr_xprop = nullptr;
+    float* tr_lpprop = nullptr; uint8_t* tr_acc = nullptr;
+    int* d_chain_changed = nullptr;
+    unsigned long long* d_counters = nullptr;   // [0] adaptγ window changed, [1] accepted proposals
+    float* dS1[2] = {nullptr, nullptr};
+    double* dS2 = nullptr;
+    float* dshift = nullptr;
+    double* d_scratch = nullptr;
+
+    // run state
+    int64_t g_done = 0;
+    double gamma = 0.0;
+    bool state_set = false, state_lp_valid = false, archive_set = false;
+    bool stopped_by_rhat = false;
+    int64_t proposals = 0;
+    std::vector<double> rhat;
+    double rhat_max = 0.0;
+    bool rhat_valid = false;
+
+    std::vector<cudaEvent_t> ev_pool;
+    cudaEvent_t ev_run[2] = {nullptr, nullptr};
+
+    // NCCL (dlopen'ed; demcz_comm.cu)
+    void* comm = nullptr;
+
+    std::string err;
+    int sticky = 0;
+};
+
+int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
+
+// demcz_comm.cu — no-ops when world == 1
+int demcz_comm_allgather_rows(demcz_ctx* c, int64_t phys_row0);
+int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n);
+int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);
+void demcz_comm_destroy_internal(demcz_ctx* c);
+
+// demcz_linreg.cu
+int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, float* out);
+int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append);
+void demcz_linreg_free(demcz_ctx* c);

@@ -1,0 +1,912 @@
+// demcz_lib.cu — libdemcz_cuda.so: context, host-side generation loop and the C ABI of
+// include/demcz.h.  Reference behaviour mirrored (file:line under the upstream repo):
+//   demcz_sample   src/demcz.jl:9-63        runchain!      src/demcz.jl:80-93
+//   demcz_anneal   src/demcz_anneal.jl:18-65 (adaptγ :48-57, tempbaseline :1-3)
+//   Rhat_gelman    src/utils.jl:2-20
+// No CPU fallback: every compute entry point needs a CUDA device.
+#include "../../include/demcz.h"
+#include "demcz_step.cuh"
+#include "demcz_internal.h"
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+using namespace demcz;
+
+static std::string g_create_error;
+
+// ------------------------------------------------------------------------------------------------
+// error plumbing
+// ------------------------------------------------------------------------------------------------
+int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) {
+        c->err = buf;
+        if (code == DEMCZ_ERR_CUDA || code == DEMCZ_ERR_NCCL) c->sticky = code;
+    } else {
+        g_create_error = buf;
+    }
+    return code;
+}
+
+#define CU(c, call)                                                                                   \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return demcz_fail((c), e_ == cudaErrorMemoryAllocation ? DEMCZ_ERR_OOM : DEMCZ_ERR_CUDA,  \
+                              "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+#define CHECK_CTX(c)                                                                    \
+    do {                                                                                \
+        if (!(c)) return DEMCZ_ERR_INVALID;                                             \
+        if ((c)->sticky) return (c)->sticky;                                            \
+        if (cudaSetDevice((c)->device) != cudaSuccess)                                  \
+            return demcz_fail((c), DEMCZ_ERR_CUDA, "cudaSetDevice(%d) failed", (c)->device); \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// small layout / reduction kernels
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+// Julia column-major Float64 (rows x d, leading dim ldin) -> archive rows (row-major, stride LD, FP32)
+__global__ void import_rows_kernel(const double* __restrict__ in, long long rows, long long ldin, int d, int LD,
+                                   float* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    for (int k = 0; k < LD; ++k) out[i * LD + k] = k < d ? (float)in[i + ldin * k] : 0.f;
+}
+
+__global__ void export_rows_kernel(const float* __restrict__ Z, long long rows, long long zstart, long long zcap,
+                                   int d, int LD, double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    long long p = zstart + i;
+    if (p >= zcap) p -= zcap;
+    for (int k = 0; k < d; ++k) out[i + rows * k] = (double)Z[p * LD + k];
+}
+
+// column-major Float64 (n x d) <-> SoA FP32 [k][ldx]
+__global__ void import_soa_kernel(const double* __restrict__ in, long long n, int d, long long ldx, float* __restrict__ X)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < d; ++k) X[k * ldx + i] = (float)in[i + n * k];
+}
+
+__global__ void export_soa_kernel(const float* __restrict__ X, long long n, int d, long long ldx, double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < d; ++k) out[i + n * k] = (double)X[k * ldx + i];
+}
+
+__global__ void f32_to_f64_kernel(const float* __restrict__ in, long long n, double* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (double)in[i];
+}
+
+__global__ void f64_to_f32_kernel(const double* __restrict__ in, long long n, float* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (float)in[i];
+}
+
+// X = Zmat[M-N+1:M, :]  (src/demcz.jl:15 as intended, :113): archive rows -> SoA state
+__global__ void rows_to_soa_kernel(const float* __restrict__ Z, long long row0, long long zcap, int n, int d, int LD,
+                                   int ldx, float* __restrict__ X)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    long long p = row0 + i;
+    if (p >= zcap) p -= zcap;
+    for (int k = 0; k < d; ++k) X[(size_t)k * ldx + i] = Z[p * LD + k];
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sm)
+{
+    v = warp_sum(v);
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    __syncthreads();
+    if (lane == 0) sm[w] = v;
+    __syncthreads();
+    double t = 0.0;
+    if (w == 0) {
+        t = lane < (int)(blockDim.x >> 5) ? sm[lane] : 0.0;
+        t = warp_sum(t);
+    }
+    return t;   // valid on thread 0
+}
+
+// sums[k] += sum_i X[k][i]   (grid: (blocks, d))
+__global__ void colsum_kernel(const float* __restrict__ X, int n, int ldx, double* __restrict__ sums)
+{
+    __shared__ double sm[32];
+    const int k = blockIdx.y;
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += X[(size_t)k * ldx + i];
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) atomicAdd(&sums[k], s);
+}
+
+__global__ void shift_from_sums_kernel(const double* __restrict__ sums, int d, double inv_n, float* __restrict__ shift,
+                                       double* __restrict__ mean_out)
+{
+    const int k = threadIdx.x;
+    if (k < d) {
+        if (shift) shift[k] = (float)(sums[k] * inv_n);
+        if (mean_out) mean_out[k] = sums[k] * inv_n;
+    }
+}
+
+// cov[k1][k2] += sum_i (x1 - m1)(x2 - m2)    (grid: (blocks, d*d))
+__global__ void cov_kernel(const float* __restrict__ X, int n, int ldx, int d, const double* __restrict__ mean,
+                           double* __restrict__ cov)
+{
+    __shared__ double sm[32];
+    const int k1 = blockIdx.y / d, k2 = blockIdx.y % d;
+    const double m1 = mean[k1], m2 = mean[k2];
+    double s = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        s += ((double)X[(size_t)k1 * ldx + i] - m1) * ((double)X[(size_t)k2 * ldx + i] - m2);
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) atomicAdd(&cov[k1 * d + k2], s);
+}
+
+// Gelman-Rubin partial sums over the local chain-halves (Rhat_gelman, src/utils.jl:2-20):
+//   part[0*d+k] += sum_j mean_j    part[1*d+k] += sum_j mean_j^2    part[2*d+k] += sum_j S1_j^2
+// with mean_j = shift + S1_j/n.  Warp-shuffle -> block -> one FP64 atomic per block.
+// grid: (blocks, d, 2 halves)
+__global__ void rhat_partial_kernel(const float* __restrict__ S1h0, const float* __restrict__ S1h1, int n_chains,
+                                    int ldx, int d, const float* __restrict__ shift, double inv_n,
+                                    double* __restrict__ part)
+{
+    __shared__ double sm[32];
+    const int k = blockIdx.y;
+    const float* S1 = blockIdx.z ? S1h1 : S1h0;
+    const double sh = shift[k];
+    double a = 0.0, b = 0.0, c = 0.0;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_chains; i += gridDim.x * blockDim.x) {
+        const double s = S1[(size_t)k * ldx + i];
+        const double m = sh + s * inv_n;
+        a += m; b += m * m; c += s * s;
+    }
+    a = block_sum(a, sm);
+    b = block_sum(b, sm);
+    c = block_sum(c, sm);
+    if (threadIdx.x == 0) {
+        atomicAdd(&part[0 * d + k], a);
+        atomicAdd(&part[1 * d + k], b);
+        atomicAdd(&part[2 * d + k], c);
+    }
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// kernel dispatch
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kWarps = 4;
+
+template <int LD>
+MvnParams<LD> make_params(const demcz_ctx* c)
+{
+    MvnParams<LD> P;
+    memset(&P, 0, sizeof P);
+    for (int k = 0; k < c->o.d; ++k) P.mu[k] = c->mvn_mu[k];
+    for (int i = 0; i < c->o.d; ++i)
+        for (int j = 0; j <= i; ++j) P.W[i * (i + 1) / 2 + j] = c->mvn_W[(size_t)i * c->o.d + j];
+    P.c0 = c->mvn_c0;
+    return P;
+}
+
+template <int LD, bool ACC, int STAGES>
+cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
+{
+    using SL = StageLayout<LD>;
+    auto kern = demcz_step_mvn_kernel<LD, ACC, kWarps, STAGES>;
+    const size_t smem = (size_t)kWarps * STAGES * SL::FLOATS * sizeof(float);
+    static bool configured = false;       // per instantiation
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        configured = true;
+    }
+    const int threads = kWarps * 32;
+    const int grid = (a.N + threads - 1) / threads;
+    const MvnParams<LD> P = make_params<LD>(c);
+    kern<<<grid, threads, smem, c->stream>>>(a, P);
+    return cudaGetLastError();
+}
+
+template <int LD>
+cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc)
+{
+    if (c->stages == 3) return acc ? launch_step_t<LD, true, 3>(c, a) : launch_step_t<LD, false, 3>(c, a);
+    return acc ? launch_step_t<LD, true, 2>(c, a) : launch_step_t<LD, false, 2>(c, a);
+}
+
+cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc)
+{
+    switch (c->LD) {
+        case 4:  return launch_step_ld<4>(c, a, acc);
+        case 8:  return launch_step_ld<8>(c, a, acc);
+        case 12: return launch_step_ld<12>(c, a, acc);
+        case 16: return launch_step_ld<16>(c, a, acc);
+        case 20: return launch_step_ld<20>(c, a, acc);
+        case 24: return launch_step_ld<24>(c, a, acc);
+        case 28: return launch_step_ld<28>(c, a, acc);
+        case 32: return launch_step_ld<32>(c, a, acc);
+    }
+    return cudaErrorInvalidValue;
+}
+
+template <int LD>
+cudaError_t launch_eval_t(demcz_ctx* c, const float* X, int n, int ldx, float* out)
+{
+    const MvnParams<LD> P = make_params<LD>(c);
+    mvn_eval_kernel<LD><<<(n + 127) / 128, 128, 0, c->stream>>>(X, n, ldx, c->o.d, out, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_eval(demcz_ctx* c, const float* X, int n, int ldx, float* out)
+{
+    switch (c->LD) {
+        case 4:  return launch_eval_t<4>(c, X, n, ldx, out);
+        case 8:  return launch_eval_t<8>(c, X, n, ldx, out);
+        case 12: return launch_eval_t<12>(c, X, n, ldx, out);
+        case 16: return launch_eval_t<16>(c, X, n, ldx, out);
+        case 20: return launch_eval_t<20>(c, X, n, ldx, out);
+        case 24: return launch_eval_t<24>(c, X, n, ldx, out);
+        case 28: return launch_eval_t<28>(c, X, n, ldx, out);
+        case 32: return launch_eval_t<32>(c, X, n, ldx, out);
+    }
+    return cudaErrorInvalidValue;
+}
+
+inline int grid1d(long long n, int threads = 256) { return (int)((n + threads - 1) / threads); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// ABI: lifecycle
+// ------------------------------------------------------------------------------------------------
+extern "C" int demcz_version(void) { return DEMCZ_VERSION; }
+
+extern "C" const char* demcz_last_error(const demcz_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
+{
+    if (!out || !o) return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: null argument");
+    *out = nullptr;
+    if (o->struct_size != (int32_t)sizeof(demcz_opts))
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: struct_size %d != %zu (ABI mismatch)", o->struct_size,
+                          sizeof(demcz_opts));
+    if (o->N < 1 || o->K < 1 || o->Ngeneration < 0 || o->d < 1 || o->Nblocks < 1 || !o->block_ptr || !o->block_idx ||
+        !o->eps_scale)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: bad N/K/Ngeneration/d/Nblocks or null arrays");
+    if (o->d > DEMCZ_MAX_DIM_LINREG)
+        return demcz_fail(nullptr, DEMCZ_ERR_UNSUPPORTED, "demcz_create: d=%d > %d", o->d, DEMCZ_MAX_DIM_LINREG);
+    if (o->Nblocks > kMaxBlocks)
+        return demcz_fail(nullptr, DEMCZ_ERR_UNSUPPORTED, "demcz_create: Nblocks=%d > %d", o->Nblocks, kMaxBlocks);
+    if (o->world < 1 || o->rank < 0 || o->rank >= o->world || o->N_global < o->N || o->chain_offset < 0 ||
+        o->chain_offset + o->N > o->N_global)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: inconsistent rank/world/N_global/chain_offset");
+    if (o->autostop && (o->autostop_every < 4))
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: autostop_every must be >= 4");
+    if (o->anneal && o->adapt && o->adapt_every < 1)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: adapt_every must be >= 1");
+    for (int b = 0; b < o->Nblocks; ++b) {
+        if (o->block_ptr[b + 1] <= o->block_ptr[b])
+            return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: empty block %d", b);
+        for (int t = o->block_ptr[b]; t < o->block_ptr[b + 1]; ++t)
+            if (o->block_idx[t] < 0 || o->block_idx[t] >= o->d)
+                return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: block %d has column %d outside 0..%d", b,
+                                  o->block_idx[t], o->d - 1);
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return demcz_fail(nullptr, DEMCZ_ERR_CUDA, "demcz_create: no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= ndev)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: device %d of %d", device, ndev);
+
+    demcz_ctx* c = new demcz_ctx();
+    c->o = *o;
+    c->device = device;
+    c->block_ptr.assign(o->block_ptr, o->block_ptr + o->Nblocks + 1);
+    c->block_idx.assign(o->block_idx, o->block_idx + o->block_ptr[o->Nblocks]);
+    c->eps.assign(o->eps_scale, o->eps_scale + o->d);
+    c->o.block_ptr = c->block_ptr.data();
+    c->o.block_idx = c->block_idx.data();
+    c->o.eps_scale = c->eps.data();
+    c->gamma = o->gamma;
+    c->LD = (o->d + 3) / 4 * 4;
+    c->ldx = (o->N + 31) / 32 * 32;
+    const char* st = getenv("DEMCZ_STAGES");
+    c->stages = (st && atoi(st) == 3) ? 3 : 2;
+    c->rhat.assign(o->d, NAN);
+
+    auto bail = [&](int code) { demcz_destroy(c); return code; };
+    if (cudaSetDevice(device) != cudaSuccess) return bail(demcz_fail(nullptr, DEMCZ_ERR_CUDA, "cudaSetDevice(%d)", device));
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+        return bail(demcz_fail(nullptr, DEMCZ_ERR_CUDA, "cudaStreamCreate"));
+    const size_t nx = (size_t)c->ldx * o->d;
+    cudaError_t e = cudaSuccess;
+    auto alloc = [&](void** p, size_t bytes) {
+        if (e == cudaSuccess) { e = cudaMalloc(p, bytes ? bytes : 16); if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes ? bytes : 16, c->stream); }
+    };
+    alloc((void**)&c->dX, nx * sizeof(float));
+    alloc((void**)&c->dlogp, (size_t)c->ldx * sizeof(float));
+    alloc((void**)&c->d_chain_changed, (size_t)c->ldx * sizeof(int));
+    alloc((void**)&c->d_counters, 4 * sizeof(unsigned long long));
+    alloc((void**)&c->d_scratch, (size_t)(8 * o->d + o->d * o->d + 16) * sizeof(double));
+    if (o->autostop) {
+        alloc((void**)&c->dS1[0], nx * sizeof(float));
+        alloc((void**)&c->dS1[1], nx * sizeof(float));
+        alloc((void**)&c->dS2, (size_t)2 * o->d * sizeof(double));
+        alloc((void**)&c->dshift, (size_t)o->d * sizeof(float));
+    }
+    if (o->store_chain && o->Ngeneration > 0) {
+        alloc((void**)&c->dhist, (size_t)o->Ngeneration * o->d * o->N * sizeof(float));
+        alloc((void**)&c->dlphist, (size_t)o->Ngeneration * o->N * sizeof(float));
+    }
+    if (o->trace && o->Ngeneration > 0) {
+        const size_t np = (size_t)o->Ngeneration * o->Nblocks * o->N;
+        alloc((void**)&c->tr_r1, np * 4); alloc((void**)&c->tr_r2, np * 4); alloc((void**)&c->tr_u, np * 4);
+        alloc((void**)&c->tr_lpprop, np * 4); alloc((void**)&c->tr_acc, np);
+        alloc((void**)&c->tr_xprop, np * o->d * 4);
+    }
+    if (e != cudaSuccess)
+        return bail(demcz_fail(nullptr, e == cudaErrorMemoryAllocation ? DEMCZ_ERR_OOM : DEMCZ_ERR_CUDA,
+                               "demcz_create: device allocation failed: %s", cudaGetErrorString(e)));
+    if (o->anneal) {   // default schedule: tempbaseline(ig, Ngeneration, T0, TN)  (src/demcz_anneal.jl:1-3; Q3)
+        std::vector<double> T((size_t)o->Ngeneration);
+        for (int ig = 1; ig <= o->Ngeneration; ++ig) T[ig - 1] = o->T0 * pow(o->TN / o->T0, (double)ig / o->Ngeneration);
+        *out = c;
+        int rc = demcz_set_temperature_table(c, T.data(), (int64_t)T.size());
+        if (rc != DEMCZ_OK) { *out = nullptr; g_create_error = c->err; return bail(rc); }
+    }
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return bail(demcz_fail(nullptr, DEMCZ_ERR_CUDA, "sync after create"));
+    *out = c;
+    return DEMCZ_OK;
+}
+
+extern "C" void demcz_destroy(demcz_ctx* c)
+{
+    if (!c) return;
+    cudaSetDevice(c->device);
+    demcz_comm_destroy_internal(c);
+    demcz_linreg_free(c);
+    void* ptrs[] = {c->dX, c->dlogp, c->dZ, c->dT, c->dhist, c->dlphist, c->tr_r1, c->tr_r2, c->tr_u, c->tr_xprop,
+                    c->tr_lpprop, c->tr_acc, c->d_chain_changed, c->d_counters, c->dS1[0], c->dS1[1], c->dS2, c->dshift,
+                    c->d_scratch};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
+    if (c->ev_run[0]) { cudaEventDestroy(c->ev_run[0]); cudaEventDestroy(c->ev_run[1]); }
+    if (c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: likelihood / archive / state
+// ------------------------------------------------------------------------------------------------
+extern "C" int demcz_set_likelihood_mvnormal(demcz_ctx* c, int32_t d, const double* mu, const double* Sigma,
+                                             int32_t drop_constant)
+{
+    CHECK_CTX(c);
+    if (!mu || !Sigma || d != c->o.d) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_likelihood_mvnormal: d=%d, opts.d=%d", d, c->o.d);
+    if (d > DEMCZ_MAX_DIM) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_likelihood_mvnormal: d=%d > %d", d, DEMCZ_MAX_DIM);
+    // FP64 Cholesky Sigma = L L^T, then W = L^-1 (lower), rounded to FP32 for the kernels
+    std::vector<double> L((size_t)d * d, 0.0), W((size_t)d * d, 0.0);
+    double logdet = 0.0;
+    for (int j = 0; j < d; ++j) {
+        double s = Sigma[j + (size_t)d * j];
+        for (int k = 0; k < j; ++k) s -= L[(size_t)j * d + k] * L[(size_t)j * d + k];
+        if (!(s > 0.0)) return demcz_fail(c, DEMCZ_ERR_NOT_PD, "set_likelihood_mvnormal: Sigma is not positive definite (pivot %d)", j);
+        const double ljj = sqrt(s);
+        L[(size_t)j * d + j] = ljj;
+        logdet += 2.0 * log(ljj);
+        for (int i = j + 1; i < d; ++i) {
+            double t = Sigma[i + (size_t)d * j];
+            for (int k = 0; k < j; ++k) t -= L[(size_t)i * d + k] * L[(size_t)j * d + k];
+            L[(size_t)i * d + j] = t / ljj;
+        }
+    }
+    for (int j = 0; j < d; ++j) {                 // columns of L^-1 by forward substitution
+        for (int i = j; i < d; ++i) {
+            double t = (i == j) ? 1.0 : 0.0;
+            for (int k = j; k < i; ++k) t -= L[(size_t)i * d + k] * W[(size_t)k * d + j];
+            W[(size_t)i * d + j] = t / L[(size_t)i * d + i];
+        }
+    }
+    c->mvn_mu.assign(d, 0.f);
+    c->mvn_W.assign((size_t)d * d, 0.f);
+    for (int k = 0; k < d; ++k) c->mvn_mu[k] = (float)mu[k];
+    for (size_t t = 0; t < (size_t)d * d; ++t) c->mvn_W[t] = (float)W[t];
+    c->mvn_c0 = drop_constant ? 0.f : (float)(-0.5 * (d * log(2.0 * M_PI) + logdet));
+    c->lik_kind = DEMCZ_LIK_MVN;
+    c->state_lp_valid = false;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
+{
+    CHECK_CTX(c);
+    if (!Z || M0 < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_archive: need at least 2 rows (got %lld)", (long long)M0);
+    const demcz_opts& o = c->o;
+    int64_t cap = o.archive_capacity > 0 ? o.archive_capacity
+                                         : M0 + (o.N_global * (int64_t)o.Ngeneration + o.K - 1) / o.K;   // src/demcz.jl:11
+    if (cap < M0) cap = M0;
+    if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
+    if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
+    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->LD * sizeof(float)));
+    c->zcap = cap;
+    c->M = M0;
+    double* stage = nullptr;
+    CU(c, cudaMalloc((void**)&stage, (size_t)M0 * o.d * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(stage, Z, (size_t)M0 * o.d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        import_rows_kernel<<<grid1d(M0), 256, 0, c->stream>>>(stage, M0, M0, o.d, c->LD, c->dZ);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    CU(c, e);
+    c->archive_set = true;
+    return DEMCZ_OK;
+}
+
+static int eval_state_logp(demcz_ctx* c)
+{
+    if (c->lik_kind == DEMCZ_LIK_MVN) {
+        CU(c, launch_eval(c, c->dX, c->o.N, c->ldx, c->dlogp));
+    } else if (c->lik_kind == DEMCZ_LIK_LINREG) {
+        int rc = demcz_linreg_eval(c, c->dX, c->o.N, c->ldx, c->dlogp);
+        if (rc != DEMCZ_OK) return rc;
+    } else {
+        return demcz_fail(c, DEMCZ_ERR_INVALID, "no likelihood set");
+    }
+    c->state_lp_valid = true;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_set_state(demcz_ctx* c, const double* X, const double* logp)
+{
+    CHECK_CTX(c);
+    if (!X) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_state: X is null");
+    const int N = c->o.N, d = c->o.d;
+    double* stage = nullptr;
+    CU(c, cudaMalloc((void**)&stage, ((size_t)N * d + N) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(stage, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        import_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage, N, d, c->ldx, c->dX);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess && logp) {
+        e = cudaMemcpyAsync(stage + (size_t)N * d, logp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+        if (e == cudaSuccess) {
+            f64_to_f32_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage + (size_t)N * d, N, c->dlogp);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    CU(c, e);
+    c->state_set = true;
+    c->state_lp_valid = logp != nullptr;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_set_temperature_table(demcz_ctx* c, const double* T, int64_t len)
+{
+    CHECK_CTX(c);
+    if (!T || len < c->o.Ngeneration) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_temperature_table: need %d entries", c->o.Ngeneration);
+    std::vector<float> Tf((size_t)len);
+    for (int64_t i = 0; i < len; ++i) Tf[i] = (float)T[i];
+    if (c->dT) { cudaFree(c->dT); c->dT = nullptr; }
+    CU(c, cudaMalloc((void**)&c->dT, (size_t)(len ? len : 1) * sizeof(float)));
+    CU(c, cudaMemcpy(c->dT, Tf.data(), (size_t)len * sizeof(float), cudaMemcpyHostToDevice));
+    return DEMCZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// the generation loop
+// ------------------------------------------------------------------------------------------------
+static int init_state_if_needed(demcz_ctx* c)
+{
+    const demcz_opts& o = c->o;
+    if (!c->state_set) {
+        if (o.init_mode == DEMCZ_INIT_REF_SERIAL_ZEROS) {           // SURVEY Q1 (src/demcz.jl:11,15)
+            CU(c, cudaMemsetAsync(c->dX, 0, (size_t)c->ldx * o.d * sizeof(float), c->stream));
+        } else {                                                    // last N rows of Z (src/demcz.jl:14 comment; :113)
+            if (c->M < o.N_global) return demcz_fail(c, DEMCZ_ERR_INVALID, "archive has %lld rows < N=%lld chains", (long long)c->M, (long long)o.N_global);
+            if (c->M > c->zcap) return demcz_fail(c, DEMCZ_ERR_INVALID, "init from a wrapped archive is not supported");
+            rows_to_soa_kernel<<<grid1d(o.N), 256, 0, c->stream>>>(c->dZ, c->M - o.N_global + o.chain_offset, c->zcap, o.N, o.d,
+                                                                   c->LD, c->ldx, c->dX);
+            CU(c, cudaGetLastError());
+        }
+        c->state_set = true;
+        c->state_lp_valid = false;
+    }
+    if (!c->state_lp_valid) return eval_state_logp(c);
+    return DEMCZ_OK;
+}
+
+static cudaEvent_t pool_event(demcz_ctx* c, size_t i)
+{
+    while (c->ev_pool.size() <= i) {
+        cudaEvent_t ev;
+        cudaEventCreate(&ev);
+        c->ev_pool.push_back(ev);
+    }
+    return c->ev_pool[i];
+}
+
+static int start_rhat_window(demcz_ctx* c)
+{
+    const demcz_opts& o = c->o;
+    const size_t nx = (size_t)c->ldx * o.d;
+    CU(c, cudaMemsetAsync(c->dS1[0], 0, nx * sizeof(float), c->stream));
+    CU(c, cudaMemsetAsync(c->dS1[1], 0, nx * sizeof(float), c->stream));
+    CU(c, cudaMemsetAsync(c->dS2, 0, (size_t)2 * o.d * sizeof(double), c->stream));
+    CU(c, cudaMemsetAsync(c->d_scratch, 0, (size_t)o.d * sizeof(double), c->stream));
+    colsum_kernel<<<dim3(std::min(grid1d(o.N), 64), o.d), 256, 0, c->stream>>>(c->dX, o.N, c->ldx, c->d_scratch);
+    shift_from_sums_kernel<<<1, 64, 0, c->stream>>>(c->d_scratch, o.d, 1.0 / o.N, c->dshift, nullptr);
+    CU(c, cudaGetLastError());
+    return DEMCZ_OK;
+}
+
+// Rhat_gelman on the finished window (src/utils.jl:2-20) from the streaming accumulators.
+static int finish_rhat_window(demcz_ctx* c, int n)
+{
+    const demcz_opts& o = c->o;
+    const int d = o.d;
+    double* part = c->d_scratch;                       // [3][d] partials, then [2][d] S2 copied behind
+    CU(c, cudaMemsetAsync(part, 0, (size_t)3 * d * sizeof(double), c->stream));
+    rhat_partial_kernel<<<dim3(std::min(grid1d(o.N), 128), d, 2), 256, 0, c->stream>>>(c->dS1[0], c->dS1[1], o.N, c->ldx, d,
+                                                                                        c->dshift, 1.0 / n, part);
+    CU(c, cudaGetLastError());
+    CU(c, cudaMemcpyAsync(part + 3 * d, c->dS2, (size_t)2 * d * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    int rc = demcz_comm_allreduce_f64(c, part, 5 * d);
+    if (rc != DEMCZ_OK) return rc;
+    std::vector<double> h((size_t)5 * d);
+    CU(c, cudaMemcpyAsync(h.data(), part, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    const double m = 2.0 * (double)o.N_global;          // m = Npop*2  (:5)
+    double mx = 0.0;
+    for (int k = 0; k < d; ++k) {
+        const double sum_mean = h[k], sum_mean2 = h[d + k], sum_s1sq = h[2 * d + k];
+        const double s2 = h[3 * d + k] + h[4 * d + k];
+        const double W = (s2 - sum_s1sq / n) / ((n - 1.0) * m);                     // :14-15
+        const double avg = sum_mean / m;                                            // :10
+        const double B = (double)n / (m - 1.0) * (sum_mean2 - m * avg * avg);       // :13
+        const double varhat = (n - 1.0) / n * W + B / n;                            // :16
+        c->rhat[k] = sqrt(varhat / W);                                              // :18
+        if (!(c->rhat[k] <= mx)) mx = c->rhat[k];                                   // NaN propagates
+    }
+    c->rhat_max = mx;
+    c->rhat_valid = true;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* info)
+{
+    CHECK_CTX(c);
+    const demcz_opts& o = c->o;
+    if (c->lik_kind == DEMCZ_LIK_NONE) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: no likelihood set");
+    if (!c->archive_set) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: no archive set");
+    if (o.world > 1 && !c->comm) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: world=%d but demcz_comm_init was not called", o.world);
+    int rc = init_state_if_needed(c);
+    if (rc != DEMCZ_OK) return rc;
+
+    if (!c->ev_run[0]) { CU(c, cudaEventCreate(&c->ev_run[0])); CU(c, cudaEventCreate(&c->ev_run[1])); }
+    CU(c, cudaEventRecord(c->ev_run[0], c->stream));
+
+    const int64_t g_begin = c->g_done;
+    int64_t g_end = o.Ngeneration;
+    if (max_generations > 0 && g_begin + max_generations < g_end) g_end = g_begin + max_generations;
+    const int every = o.autostop_every, nhalf = every / 2;
+    size_t n_launch = 0;
+    bool stopped = false;
+
+    int64_t g = g_begin;
+    while (g < g_end && !stopped) {
+        // ---- next boundary ---------------------------------------------------------------------
+        int64_t gb = std::min<int64_t>(g_end, (g / o.K + 1) * (int64_t)o.K);            // archive append
+        bool acc = false;
+        int half = 0;
+        if (o.autostop) {
+            const int64_t w0 = g / every * every;
+            const int64_t rel = g - w0;                                                 // generations of the window done
+            if (rel == 0) { rc = start_rhat_window(c); if (rc != DEMCZ_OK) return rc; }
+            if (rel < nhalf)            { gb = std::min(gb, w0 + nhalf);     acc = true; half = 0; }
+            else if (rel < 2 * nhalf)   { gb = std::min(gb, w0 + 2 * nhalf); acc = true; half = 1; }
+            else                        { gb = std::min(gb, w0 + every); }
+        }
+        if (o.anneal && o.adapt) gb = std::min<int64_t>(gb, (g / o.adapt_every + 1) * (int64_t)o.adapt_every);
+        const int n_gens = (int)(gb - g);
+        const bool append = (gb % o.K) == 0;
+
+        if (c->lik_kind == DEMCZ_LIK_LINREG) {
+            rc = demcz_linreg_generations(c, g, n_gens, append);
+            if (rc != DEMCZ_OK) return rc;
+        } else {
+            // ---- launch ------------------------------------------------------------------------
+            StepArgs a;
+            memset(&a, 0, sizeof a);
+            a.X = c->dX; a.logp = c->dlogp; a.N = o.N; a.ldx = c->ldx; a.d = o.d;
+            a.chain_offset = (uint32_t)o.chain_offset;
+            a.Z = c->dZ;
+            a.Mdraw = (uint32_t)std::min<int64_t>(c->M, c->zcap);
+            a.zcap = (uint32_t)c->zcap;
+            a.zstart = c->M > c->zcap ? (uint32_t)(c->M % c->zcap) : 0u;
+            a.gen0 = o.gen_offset + g + 1;
+            a.grel0 = g + 1;
+            a.n_gens = n_gens;
+            a.key0 = (uint32_t)o.seed; a.key1 = (uint32_t)(o.seed >> 32);
+            a.nblocks = o.Nblocks;
+            for (int b = 0; b < o.Nblocks; ++b) {
+                uint32_t mask = 0;
+                for (int t = c->block_ptr[b]; t < c->block_ptr[b + 1]; ++t) mask |= 1u << c->block_idx[t];
+                const int blocklen = c->block_ptr[b + 1] - c->block_ptr[b];
+                a.blocks[b].mask = mask;
+                a.blocks[b].cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
+            }
+            for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
+            a.Ttab = o.anneal ? c->dT : nullptr;
+            a.Zw = append ? c->dZ : nullptr;
+            a.append_row0 = (uint32_t)(c->M % c->zcap);
+            a.hist = c->dhist; a.lphist = c->dlphist;
+            a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
+            a.tr_lpprop = c->tr_lpprop; a.tr_acc = c->tr_acc;
+            a.chain_changed = c->d_chain_changed;
+            a.win_changed = c->d_counters + 0;
+            a.accepted_total = c->d_counters + 1;
+            a.run_skip_gi = (g == 0) ? 0 : -1;
+            a.win_skip_gi = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : -1;
+            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; a.shift = c->dshift; }
+
+            if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
+            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
+            CU(c, launch_step(c, a, acc));
+            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
+            ++n_launch;
+        }
+        c->proposals += (int64_t)n_gens * o.Nblocks * o.N;
+
+        // ---- archive append + exchange (src/demcz.jl:88-91; sync mode :129-137) -----------------
+        if (append) {
+            if (o.world > 1) {
+                rc = demcz_comm_allgather_rows(c, (int64_t)(c->M % c->zcap));
+                if (rc != DEMCZ_OK) return rc;
+            }
+            c->M += o.N_global;
+        }
+        g = gb;
+        c->g_done = g;
+
+        // ---- adaptγ (src/demcz_anneal.jl:48-57) --------------------------------------------------
+        if (o.anneal && o.adapt && g % o.adapt_every == 0) {
+            rc = demcz_comm_allreduce_u64(c, c->d_counters + 0, 1);
+            if (rc != DEMCZ_OK) return rc;
+            unsigned long long cnt = 0;
+            CU(c, cudaMemcpyAsync(&cnt, c->d_counters + 0, sizeof cnt, cudaMemcpyDeviceToHost, c->stream));
+            CU(c, cudaStreamSynchronize(c->stream));
+            CU(c, cudaMemsetAsync(c->d_counters + 0, 0, sizeof cnt, c->stream));
+            const double ar = (double)cnt / ((double)o.N_global * o.adapt_every);
+            if (ar < 0.1) c->gamma = std::max(o.min_gamma, c->gamma * 0.5);
+            else if (ar > 0.5) c->gamma = std::min(o.max_gamma, c->gamma * 1.5);
+        }
+        // ---- Rhat autostop (src/demcz.jl:39-55) --------------------------------------------------
+        if (o.autostop && !o.anneal && g % every == 0) {
+            rc = finish_rhat_window(c, nhalf);
+            if (rc != DEMCZ_OK) return rc;
+            if (c->rhat_max < o.autostop_Rhat) stopped = true;
+        }
+    }
+    CU(c, cudaEventRecord(c->ev_run[1], c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (stopped) c->stopped_by_rhat = true;
+
+    if (info) {
+        memset(info, 0, sizeof *info);
+        info->generations_done = c->g_done - g_begin;
+        info->generations_total = c->g_done;
+        info->stopped_by_rhat = stopped ? 1 : 0;
+        info->rhat_valid = c->rhat_valid ? 1 : 0;
+        info->rhat_max = c->rhat_valid ? c->rhat_max : NAN;
+        info->final_gamma = c->gamma;
+        info->M = c->M;
+        info->proposals = c->proposals;
+        unsigned long long acc_total = 0;
+        CU(c, cudaMemcpy(&acc_total, c->d_counters + 1, sizeof acc_total, cudaMemcpyDeviceToHost));
+        info->accepted = (int64_t)acc_total;
+        info->step_launches = (int64_t)n_launch;
+        float ms = 0.f;
+        CU(c, cudaEventElapsedTime(&ms, c->ev_run[0], c->ev_run[1]));
+        info->device_ms = ms;
+        if (o.profile) {
+            double tot = 0.0;
+            for (size_t i = 0; i < n_launch; ++i) {
+                float t = 0.f;
+                CU(c, cudaEventElapsedTime(&t, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]));
+                tot += t;
+            }
+            info->step_kernel_ms = tot;
+        }
+    }
+    return DEMCZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// ABI: results
+// ------------------------------------------------------------------------------------------------
+static int d2h_as_f64(demcz_ctx* c, const float* src, size_t n, double* dst)
+{
+    double* stage = nullptr;
+    CU(c, cudaMalloc((void**)&stage, n * sizeof(double)));
+    f32_to_f64_kernel<<<grid1d((long long)n), 256, 0, c->stream>>>(src, (long long)n, stage);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dst, stage, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    CU(c, e);
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_chain(demcz_ctx* c, double* chain, double* log_obj)
+{
+    CHECK_CTX(c);
+    if (!c->o.store_chain || !c->dhist) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: store_chain was 0");
+    const size_t G = (size_t)c->g_done, N = c->o.N, d = c->o.d;
+    if (G == 0) return DEMCZ_OK;
+    // device history is [g][k][chain] in FP32 == Julia's column-major N x d x G
+    if (chain) { int rc = d2h_as_f64(c, c->dhist, G * d * N, chain); if (rc) return rc; }
+    if (log_obj) { int rc = d2h_as_f64(c, c->dlphist, G * N, log_obj); if (rc) return rc; }
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_state(demcz_ctx* c, double* X, double* logp)
+{
+    CHECK_CTX(c);
+    if (!c->state_set) { int rc = init_state_if_needed(c); if (rc) return rc; }
+    const int N = c->o.N, d = c->o.d;
+    double* stage = nullptr;
+    CU(c, cudaMalloc((void**)&stage, ((size_t)N * d + N) * sizeof(double)));
+    export_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dX, N, d, c->ldx, stage);
+    f32_to_f64_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dlogp, N, stage + (size_t)N * d);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess && X) e = cudaMemcpyAsync(X, stage, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess && logp) e = cudaMemcpyAsync(logp, stage + (size_t)N * d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    CU(c, e);
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_archive(demcz_ctx* c, double* Z, int64_t* M)
+{
+    CHECK_CTX(c);
+    if (!c->archive_set) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_archive: no archive");
+    const int64_t rows = std::min<int64_t>(c->M, c->zcap);
+    if (M) *M = rows;
+    if (!Z) return DEMCZ_OK;
+    double* stage = nullptr;
+    CU(c, cudaMalloc((void**)&stage, (size_t)rows * c->o.d * sizeof(double)));
+    const int64_t zstart = c->M > c->zcap ? c->M % c->zcap : 0;
+    export_rows_kernel<<<grid1d(rows), 256, 0, c->stream>>>(c->dZ, rows, zstart, c->zcap, c->o.d, c->LD, stage);
+    cudaError_t e = cudaGetLastError();
+    if (e == cudaSuccess) e = cudaMemcpyAsync(Z, stage, (size_t)rows * c->o.d * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    CU(c, e);
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_moments(demcz_ctx* c, double* mean, double* cov)
+{
+    CHECK_CTX(c);
+    const int d = c->o.d, N = c->o.N;
+    double* sums = c->d_scratch;            // [d] sums, [d] mean, [d*d] cov
+    double* dmean = sums + d;
+    double* dcov = dmean + d;
+    CU(c, cudaMemsetAsync(sums, 0, (size_t)(2 * d + d * d) * sizeof(double), c->stream));
+    colsum_kernel<<<dim3(std::min(grid1d(N), 64), d), 256, 0, c->stream>>>(c->dX, N, c->ldx, sums);
+    int rc = demcz_comm_allreduce_f64(c, sums, d);
+    if (rc) return rc;
+    shift_from_sums_kernel<<<1, 64, 0, c->stream>>>(sums, d, 1.0 / (double)c->o.N_global, nullptr, dmean);
+    cov_kernel<<<dim3(std::min(grid1d(N), 64), d * d), 256, 0, c->stream>>>(c->dX, N, c->ldx, d, dmean, dcov);
+    CU(c, cudaGetLastError());
+    rc = demcz_comm_allreduce_f64(c, dcov, d * d);
+    if (rc) return rc;
+    std::vector<double> h((size_t)d + d * d);
+    CU(c, cudaMemcpyAsync(h.data(), dmean, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (mean) for (int k = 0; k < d; ++k) mean[k] = h[k];
+    if (cov) for (int t = 0; t < d * d; ++t) cov[t] = h[d + t] / (double)c->o.N_global;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_rhat(demcz_ctx* c, double* rhat)
+{
+    CHECK_CTX(c);
+    if (!rhat) return DEMCZ_ERR_INVALID;
+    for (int k = 0; k < c->o.d; ++k) rhat[k] = c->rhat[k];
+    return c->rhat_valid ? DEMCZ_OK : demcz_fail(c, DEMCZ_ERR_INVALID, "get_rhat: no Rhat window finished yet");
+}
+
+extern "C" int demcz_get_accept_counts(demcz_ctx* c, int64_t* per_chain)
+{
+    CHECK_CTX(c);
+    if (!per_chain) return DEMCZ_ERR_INVALID;
+    std::vector<int> h((size_t)c->o.N);
+    CU(c, cudaMemcpy(h.data(), c->d_chain_changed, h.size() * sizeof(int), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < h.size(); ++i) per_chain[i] = h[i];
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_eval_logdensity(demcz_ctx* c, const double* X, int64_t n, double* out)
+{
+    CHECK_CTX(c);
+    if (!X || !out || n < 1) return demcz_fail(c, DEMCZ_ERR_INVALID, "eval_logdensity: bad arguments");
+    if (c->lik_kind == DEMCZ_LIK_NONE) return demcz_fail(c, DEMCZ_ERR_INVALID, "eval_logdensity: no likelihood set");
+    const int d = c->o.d;
+    const int64_t ld = (n + 31) / 32 * 32;
+    double* stage = nullptr;
+    float* xf = nullptr;
+    CU(c, cudaMalloc((void**)&stage, (size_t)n * (d + 1) * sizeof(double)));
+    cudaError_t e = cudaMalloc((void**)&xf, (size_t)ld * (d + 1) * sizeof(float));
+    int rc = DEMCZ_OK;
+    if (e == cudaSuccess) e = cudaMemsetAsync(xf, 0, (size_t)ld * (d + 1) * sizeof(float), c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(stage, X, (size_t)n * d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) {
+        import_soa_kernel<<<grid1d(n), 256, 0, c->stream>>>(stage, n, d, ld, xf);
+        float* of = xf + (size_t)ld * d;
+        if (c->lik_kind == DEMCZ_LIK_MVN) e = launch_eval(c, xf, (int)n, (int)ld, of);
+        else rc = demcz_linreg_eval(c, xf, (int)n, (int)ld, of);
+        if (e == cudaSuccess && rc == DEMCZ_OK) {
+            f32_to_f64_kernel<<<grid1d(n), 256, 0, c->stream>>>(of, n, stage + (size_t)n * d);
+            e = cudaGetLastError();
+        }
+    }
+    if (e == cudaSuccess && rc == DEMCZ_OK) e = cudaMemcpyAsync(out, stage + (size_t)n * d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(stage);
+    if (xf) cudaFree(xf);
+    if (rc != DEMCZ_OK) return rc;
+    CU(c, e);
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_trace(demcz_ctx* c, uint32_t* r1, uint32_t* r2, float* u, float* xprop, float* lp_prop,
+                               uint8_t* accepted)
+{
+    CHECK_CTX(c);
+    if (!c->o.trace || !c->tr_r1) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_trace: trace was 0");
+    const size_t np = (size_t)c->g_done * c->o.Nblocks * c->o.N;
+    if (np == 0) return DEMCZ_OK;
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (r1) CU(c, cudaMemcpy(r1, c->tr_r1, np * 4, cudaMemcpyDeviceToHost));
+    if (r2) CU(c, cudaMemcpy(r2, c->tr_r2, np * 4, cudaMemcpyDeviceToHost));
+    if (u) CU(c, cudaMemcpy(u, c->tr_u, np * 4, cudaMemcpyDeviceToHost));
+    if (lp_prop) CU(c, cudaMemcpy(lp_prop, c->tr_lpprop, np * 4, cudaMemcpyDeviceToHost));
+    if (accepted) CU(c, cudaMemcpy(accepted, c->tr_acc, np, cudaMemcpyDeviceToHost));
+    if (xprop) CU(c, cudaMemcpy(xprop, c->tr_xprop, np * c->o.d * 4, cudaMemcpyDeviceToHost));
+    return DEMCZ_OK;
+}

@@ -125,46 +125,57 @@ class LinRegLik:
 # One generation, all chains, generation-synchronous archive (update_blocks ->
 # update_demcz_chain_block -> accept: src/demcz.jl:167-203; tempered: src/demcz_anneal.jl:142-178)
 # ------------------------------------------------------------------------------------------------
-def generation(X, lp, Z, M, lik, blocks, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0):
-    """X (N,d), lp (N,) are NOT modified; returns (Xnew, lpnew, trace).
+def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0):
+    """update_demcz_chain_block for every chain (src/demcz.jl:174-195; tempered src/demcz_anneal.jl:149-170).
 
-    Z: (>=M, d) array, first M rows valid.  blocks: list of 0-based index arrays.
-    T None -> plain accept (src/demcz.jl:198); else tempered (src/demcz_anneal.jl:173).
-    """
-    X = np.array(X, dtype=np.float64)
-    lp = np.array(lp, dtype=np.float64)
+    X (N,d), lp (N,) are the states ENTERING block ib; returns a dict with r1, r2, u, xprop, lp_prop,
+    accepted and margin = (lp_prop - lp) - T*log(u)  (accept <=> margin > 0; T=1 when T is None)."""
+    X = np.asarray(X, dtype=np.float64)
+    lp = np.asarray(lp, dtype=np.float64)
     N, d = X.shape
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
     cid = np.arange(N, dtype=np.uint64) + np.uint64(chain_offset)
+    block = np.asarray(block, dtype=np.int64)
+    w = philox4x32_10(counters(cid, gen_abs, ib, 0), key)
+    r1, r2 = draw_pair(w[:, 0], w[:, 1], M)                                # :176-179
+    blocklen = block.size
+    c = gamma if blocklen == 1 else gamma / math.sqrt(2.0 * blocklen)      # :183-187
+    zn = {}
+    Xp = X.copy()                                                          # de_diffvec = zeros :180
+    for k in block:
+        q = int(k) >> 2
+        if q not in zn:                                                    # randn(blocklen) :186
+            wn = philox4x32_10(counters(cid, gen_abs, ib, 1 + q), key)
+            z0, z1 = box_muller(wn[:, 0], wn[:, 1])
+            z2, z3 = box_muller(wn[:, 2], wn[:, 3])
+            zn[q] = (z0, z1, z2, z3)
+        diff = c * (Z[r1, k] - Z[r2, k]) + eps_scale[k] * zn[q][int(k) & 3]
+        Xp[:, k] = X[:, k] + diff                                          # :188
+    lpp = lik.logdensity(Xp)                                               # :189
+    u = uniform(w[:, 2])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        if T is None:
+            acc = np.log(u) < (lpp - lp)                                   # :198
+            margin = (lpp - lp) - np.log(u)
+        else:
+            acc = np.log(u) < (lpp - lp) / T                               # anneal :173
+            margin = (lpp - lp) - T * np.log(u)
+    return dict(r1=r1, r2=r2, u=u, xprop=Xp, lp_prop=lpp, accepted=acc, margin=margin)
+
+
+def generation(X, lp, Z, M, lik, blocks, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0):
+    """update_blocks for every chain, generation-synchronous archive (src/demcz.jl:167-172).
+    X (N,d), lp (N,) are NOT modified; returns (Xnew, lpnew, trace[block])."""
+    X = np.array(X, dtype=np.float64)
+    lp = np.array(lp, dtype=np.float64)
     tr = {k: [] for k in ("r1", "r2", "u", "xprop", "lp_prop", "accepted")}
     for ib, block in enumerate(blocks):                                    # :168
-        block = np.asarray(block, dtype=np.int64)
-        w = philox4x32_10(counters(cid, gen_abs, ib, 0), key)
-        r1, r2 = draw_pair(w[:, 0], w[:, 1], M)                            # :176-179
-        blocklen = block.size
-        c = gamma if blocklen == 1 else gamma / math.sqrt(2.0 * blocklen)  # :183-187
-        zn = {}
-        Xp = X.copy()                                                      # de_diffvec = zeros :180
-        for k in block:
-            q = int(k) >> 2
-            if q not in zn:                                                # randn(blocklen) :186
-                wn = philox4x32_10(counters(cid, gen_abs, ib, 1 + q), key)
-                z0, z1 = box_muller(wn[:, 0], wn[:, 1])
-                z2, z3 = box_muller(wn[:, 2], wn[:, 3])
-                zn[q] = (z0, z1, z2, z3)
-            diff = c * (Z[r1, k] - Z[r2, k]) + eps_scale[k] * zn[q][int(k) & 3]
-            Xp[:, k] = X[:, k] + diff                                      # :188
-        lpp = lik.logdensity(Xp)                                           # :189
-        u = uniform(w[:, 2])
-        with np.errstate(divide="ignore", invalid="ignore"):
-            if T is None:
-                acc = np.log(u) < (lpp - lp)                               # :198
-            else:
-                acc = np.log(u) < (lpp - lp) / T                           # anneal :173
-        for name, val in (("r1", r1), ("r2", r2), ("u", u), ("xprop", Xp), ("lp_prop", lpp), ("accepted", acc)):
-            tr[name].append(np.array(val))
-        X[acc] = Xp[acc]                                                   # :190-194
-        lp[acc] = lpp[acc]
+        b = block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T, chain_offset)
+        for name in tr:
+            tr[name].append(np.array(b[name]))
+        acc = b["accepted"]
+        X[acc] = b["xprop"][acc]                                           # :190-194
+        lp[acc] = b["lp_prop"][acc]
     return X, lp, {k: np.stack(v) for k, v in tr.items()}
 
 
