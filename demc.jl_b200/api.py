@@ -234,6 +234,9 @@ class Sampler:
         self.generations_total = info.generations_total
         return {k: getattr(info, k) for k, _ in _lib.RunInfo._fields_}
 
+    def set_profile(self, on=True):
+        self._check(self.lib.demcz_set_profile(self.ctx, int(bool(on))))
+
     # -- outputs -----------------------------------------------------------------------------
     def get_chain(self):
         G = self.generations_total

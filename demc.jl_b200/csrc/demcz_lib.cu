@@ -754,6 +754,13 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     return DEMCZ_OK;
 }
 
+extern "C" int demcz_set_profile(demcz_ctx* c, int32_t on)
+{
+    CHECK_CTX(c);
+    c->o.profile = on ? 1 : 0;
+    return DEMCZ_OK;
+}
+
 // ------------------------------------------------------------------------------------------------
 // ABI: results
 // ------------------------------------------------------------------------------------------------
@@ -785,7 +792,8 @@ extern "C" int demcz_get_chain(demcz_ctx* c, double* chain, double* log_obj)
 extern "C" int demcz_get_state(demcz_ctx* c, double* X, double* logp)
 {
     CHECK_CTX(c);
-    if (!c->state_set) { int rc = init_state_if_needed(c); if (rc) return rc; }
+    if (!c->state_set && !c->archive_set) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_state: no state and no archive");
+    { int rc = init_state_if_needed(c); if (rc) return rc; }   // also evaluates logp after set_state(X, NULL)
     const int N = c->o.N, d = c->o.d;
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, ((size_t)N * d + N) * sizeof(double)));

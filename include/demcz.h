@@ -126,6 +126,9 @@ int demcz_set_temperature_table(demcz_ctx* ctx, const double* T, int64_t len);
  * (src/demcz.jl:30-56, 80-93, 167-203; src/demcz_anneal.jl:39-58, 67-80, 142-178).
  * Runs up to max_generations more generations (<=0: all remaining). Blocking. */
 int demcz_run(demcz_ctx* ctx, int64_t max_generations, demcz_run_info* info);
+/* measurement switch (no reference counterpart): 1 = bracket every step-kernel launch of later
+ * demcz_run calls with CUDA events on the context's stream (demcz_run_info.step_kernel_ms). */
+int demcz_set_profile(demcz_ctx* ctx, int32_t on);
 
 /* replaces: the MC result struct (src/DEMC.jl:10-15).  chain: N x d x G, log_obj: N x G
  * (G = generations_total), column-major Float64.  Needs store_chain=1. */

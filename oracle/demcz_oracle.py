@@ -379,11 +379,14 @@ class COracle:
         info = _RunInfo()
         X0f = np.asfortranarray(X0, dtype=np.float64) if X0 is not None else None
         lp0f = np.ascontiguousarray(lp0, dtype=np.float64) if lp0 is not None else None
+        import time
+        t0 = time.perf_counter()
         rc = self.lib.orc_run(C.byref(o), C.byref(r), C.byref(s), _ptr(Z), C.c_int64(cap), C.c_int64(M0), _ptr(X0f),
                               _ptr(lp0f), _ptr(chain), _ptr(log_obj), _ptr(Xout), _ptr(lpout), _ptr(rhat),
                               C.byref(info))
+        seconds = time.perf_counter() - t0
         assert rc == 0
         g = info.generations_done
         return dict(chain=chain[:, :, :g] if store_chain else None, log_obj=log_obj[:, :g] if store_chain else None,
                     X=Xout, lp=lpout, Z=np.array(Z[:info.M]), M=info.M, generations=g,
-                    stopped_by_rhat=bool(info.stopped_by_rhat), gamma=info.final_gamma, rhat=rhat)
+                    stopped_by_rhat=bool(info.stopped_by_rhat), gamma=info.final_gamma, rhat=rhat, seconds=seconds)

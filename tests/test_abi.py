@@ -1,0 +1,100 @@
+"""CPU-side checks of the drop-in boundary: libdemcz_cuda.so loads, exports every symbol that
+include/demcz.h declares, its POD structs match the ctypes mirror, and — with no CUDA device —
+the product path fails loudly instead of falling back to anything on the CPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+import demc_jl_b200 as DEMC
+from demc_jl_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = torch.cuda.is_available()
+
+
+def _header_functions():
+    src = open(os.path.join(ROOT, "include", "demcz.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(demcz_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _header_functions()
+    assert len(names) >= 20
+    for n in names:
+        assert hasattr(lib, n), f"libdemcz_cuda.so does not export {n}"
+    assert sorted(_lib.EXPORTS) == names
+
+
+def test_version_and_struct_sizes():
+    lib = _lib.load()
+    assert lib.demcz_version() == 100
+    # the library rejects a mismatching struct_size: proves both sides agree on sizeof(demcz_opts)
+    o = _lib.Opts()
+    o.struct_size = C.sizeof(_lib.Opts) - 4
+    ctx = C.c_void_p()
+    assert lib.demcz_create(C.byref(ctx), C.byref(o), 0) == -1
+    assert b"struct_size" in lib.demcz_last_error(None)
+
+
+def test_create_validates_arguments_before_touching_cuda():
+    lib = _lib.load()
+    bp = np.array([0, 2], dtype=np.int32)
+    bi = np.array([0, 5], dtype=np.int32)          # column 5 outside d=2
+    eps = np.ones(2)
+    o = _lib.Opts()
+    o.struct_size = C.sizeof(_lib.Opts)
+    o.N, o.K, o.Ngeneration, o.Nblocks, o.d = 4, 10, 10, 1, 2
+    o.block_ptr = bp.ctypes.data_as(C.POINTER(C.c_int32))
+    o.block_idx = bi.ctypes.data_as(C.POINTER(C.c_int32))
+    o.eps_scale = eps.ctypes.data_as(C.POINTER(C.c_double))
+    o.rank, o.world, o.N_global = 0, 1, 4
+    ctx = C.c_void_p()
+    assert lib.demcz_create(C.byref(ctx), C.byref(o), 0) == -1
+    assert b"outside" in lib.demcz_last_error(None)
+
+
+@pytest.mark.skipif(HAS_GPU, reason="checks the no-GPU failure mode")
+def test_no_gpu_means_loud_failure_not_cpu_fallback():
+    mu = np.zeros(3)
+    with pytest.raises(_lib.DemczError) as ei:
+        DEMC.demcz_sample(DEMC.MvNormalLogpdf(mu, np.eye(3)), np.random.default_rng(0).normal(size=(30, 3)),
+                          4, 10, 20, 1, [[0, 1, 2]], 1e-4 * np.ones(3), 2.38, verbose=False)
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_closure_logobj_is_rejected():
+    with pytest.raises(TypeError):
+        DEMC.demcz_sample(lambda x: -np.sum(x * x), np.zeros((10, 2)), DEMC.demcopt(2))
+
+
+def test_demcopt_defaults_match_reference():
+    # src/DEMC.jl:41-43
+    o = DEMC.demcopt(7)
+    assert (o.N, o.K, o.Ngeneration, o.Nblocks) == (4, 10, 5000, 1)
+    assert o.blockindex == [list(range(7))]
+    np.testing.assert_array_equal(o.eps_scale, 1e-4 * np.ones(7))
+    assert (o.γ, o.verbose, o.print_step, o.T0, o.TN) == (2.38, True, 100, 3, 1e-3)
+    assert (o.autostop, o.autostop_every, o.autostop_Rhat) == ("Rhat", 1000, 1.05)
+    o.γ = 2.0
+    assert o.gamma == 2.0
+
+
+def test_host_diagnostics_match_oracle():
+    from oracle import demcz_oracle as orc
+    rng = np.random.default_rng(0)
+    chain = rng.normal(size=(6, 3, 41)) + rng.normal(size=(6, 3, 1))
+    np.testing.assert_allclose(DEMC.Rhat_gelman(chain), orc.rhat_gelman(chain), rtol=1e-13)
+    np.testing.assert_array_equal(DEMC.flatten_chain(chain), orc.flatten_chain(chain))
+    b, c = DEMC.mean_cov_chain(chain)
+    b2, c2 = orc.mean_cov_chain(chain)
+    np.testing.assert_allclose(b, b2)
+    np.testing.assert_allclose(c, c2)
+    lo = rng.integers(0, 3, size=(6, 41)).astype(float)
+    ar, rh = DEMC.convergence_check(chain, lo, verbose=False)
+    np.testing.assert_array_equal(ar, orc.accept_ratio(lo))

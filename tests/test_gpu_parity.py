@@ -1,0 +1,221 @@
+"""GPU parity tests proper (-m gpu): the CUDA generation loop, called through the C ABI, against
+the CPU oracle on the same seeded inputs — see tests/parity.py for the comparison rules."""
+import numpy as np
+import pytest
+import scipy.stats
+
+import demc_jl_b200 as DEMC
+from demc_jl_b200 import _lib
+from oracle import demcz_oracle as orc
+from tests.parity import check_run_against_oracle, example_normpdf_target
+
+pytestmark = pytest.mark.gpu
+
+
+def _z0(rows, d, seed=1, scale=1.0):
+    return scale * np.random.default_rng(seed).normal(size=(rows, d))
+
+
+def test_config1_normpdf_stepwise():
+    # BASELINE configs[0]: test/example_normpdf.jl — d=5 MvNormal, N=100, K=10
+    d, N = 5, 100
+    mu, S = example_normpdf_target(d)
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N=N, K=10, G=60,
+                                  blocks=[list(range(d))], eps=1e-5 * np.ones(d), gamma=2.38, seed=31953150)
+    assert st["proposals"] == 100 * 60 and st["band_disagree"] <= st["in_band"]
+
+
+@pytest.mark.parametrize("d,N,K,blocks", [
+    (5, 77, 7, [[0, 1, 2], [3], [4]]),            # ragged N, blocklen-1 blocks
+    (5, 33, 3, [[4, 2], [0, 1, 3]]),              # non-contiguous blocks
+    (1, 40, 5, [[0]]),                            # scalar parameter
+    (10, 256, 10, [list(range(5)), list(range(5, 10))]),
+    (20, 1000, 10, [list(range(20))]),
+    (32, 64, 4, [list(range(16)), list(range(16, 32))]),   # DEMCZ_MAX_DIM
+    (7, 31, 1, [[0, 1, 2, 3, 4, 5, 6]]),          # K=1: append every generation
+])
+def test_shapes_and_blocks_stepwise(d, N, K, blocks):
+    mu, S = example_normpdf_target(d, seed=d)
+    eps = 1e-3 * (1 + np.arange(d))
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(3 * N + 11, d, seed=N, scale=0.3), N=N, K=K, G=24,
+                                  blocks=blocks, eps=eps, gamma=2.38, seed=12345 + d)
+    assert st["accepted"] > 0
+
+
+def test_correlated_d20_stepwise():
+    # BASELINE configs[3] target: 20-dim highly correlated MvNormal
+    d, N = 20, 512
+    S = 0.95 * np.ones((d, d)) + 0.05 * np.eye(d)
+    mu = np.linspace(-1, 1, d)
+    Z0 = np.random.default_rng(3).multivariate_normal(mu, S, size=4 * N)
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), Z0, N=N, K=10, G=30, blocks=[list(range(d))],
+                                  eps=1e-5 * np.ones(d), gamma=2.38, seed=7)
+    assert 0.05 < st["accept_frac"] < 0.6
+
+
+@pytest.mark.parametrize("TN", [1e-4, 0.0])
+def test_anneal_config3_stepwise(TN):
+    # BASELINE configs[2]: test/test_anneal.jl — quadratic objective, d=10, Nblocks=2; TN=0 is SURVEY Q4
+    d, N = 10, 200
+    mu = np.random.default_rng(2).random(d)
+    st = check_run_against_oracle(DEMC.QuadraticLogobj(mu), _z0(10 * d + N, d), N=N, K=10, G=40,
+                                  blocks=[list(range(5)), list(range(5, 10))], eps=1e-5 * np.ones(d), gamma=2.38,
+                                  seed=99, anneal=True, T0=2.0, TN=TN)
+    assert st["accepted"] > 0
+
+
+def test_custom_temperature_table_and_quirk_Q3():
+    # serial reference quirk Q3: T = 1e-3^(ig/1000) whatever opts say — reproducible through the table
+    d, N, G = 4, 64, 20
+    mu = np.zeros(d)
+    T = np.array([orc.tempbaseline(ig, 1000, 1.0, 1e-3) for ig in range(1, G + 1)])
+    check_run_against_oracle(DEMC.QuadraticLogobj(mu), _z0(2 * N, d), N=N, K=5, G=G, blocks=[list(range(d))],
+                             eps=1e-4 * np.ones(d), gamma=2.38, seed=5, anneal=True, Ttable=T)
+
+
+def test_init_modes_and_gen_offset_and_chunked_run():
+    d, N = 5, 48
+    mu, S = example_normpdf_target(d)
+    lo = DEMC.MvNormalLogpdf(mu, S)
+    kw = dict(N=N, K=10, G=30, blocks=[list(range(d))], eps=1e-5 * np.ones(d), gamma=2.38, seed=3)
+    check_run_against_oracle(lo, _z0(60, d), init_mode="ref_serial_zeros", **kw)
+    check_run_against_oracle(lo, _z0(60, d), gen_offset=2**33 + 17, **kw)               # 64-bit generation counter
+    check_run_against_oracle(lo, _z0(60, d), chunks=[7, 1, 12], **kw)                   # resume inside a context
+    X0 = mu + 0.01 * np.random.default_rng(5).normal(size=(N, d))
+    check_run_against_oracle(lo, _z0(60, d), X0=X0, **kw)                               # prevrun-style state
+
+
+def test_prevrun_continuation_is_bit_identical():
+    # mc, Z = demcz_sample(...); mc, Z = demcz_sample(..., Z; prevrun=mc)   (test/example_normpdf.jl:30-32)
+    d, N, K = 5, 20, 10
+    mu, S = example_normpdf_target(d)
+    lo = DEMC.MvNormalLogpdf(mu, S)
+    args = (N, K, 40, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38)
+    Z0 = _z0(50, d)
+    mc_full, Z_full = DEMC.demcz_sample(lo, Z0, *args, verbose=False)
+    args2 = (N, K, 20, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38)
+    mc1, Z1 = DEMC.demcz_sample(lo, Z0, *args2, verbose=False)
+    mc2, Z2 = DEMC.demcz_sample(lo, Z1, *args2, prevrun=mc1, verbose=False)
+    assert mc2.chain.shape == (N, d, 40)
+    np.testing.assert_array_equal(mc2.chain, mc_full.chain)
+    np.testing.assert_array_equal(mc2.log_obj, mc_full.log_obj)
+    np.testing.assert_array_equal(Z2, Z_full)
+
+
+def test_eval_logdensity_vs_scipy():
+    for d in (1, 5, 20, 32):
+        mu, S = example_normpdf_target(d, seed=d)
+        X = mu + 0.2 * np.random.default_rng(d).normal(size=(1000, d))
+        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=4, K=10, Ngeneration=1, blockindex=[list(range(d))],
+                          eps_scale=np.ones(d), γ=2.38) as s:
+            got = s.eval_logdensity(X)
+        ref = scipy.stats.multivariate_normal(mu, S).logpdf(X)
+        np.testing.assert_allclose(got, ref, rtol=1e-5)
+
+
+def test_error_paths():
+    d = 3
+    with pytest.raises(_lib.DemczError) as ei:
+        DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(d), -np.eye(d)), d, N=4, K=10, Ngeneration=1,
+                     blockindex=[list(range(d))], eps_scale=np.ones(d), γ=2.38)
+    assert ei.value.code == -5                              # DEMCZ_ERR_NOT_PD
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(d), np.eye(d)), d, N=4, K=10, Ngeneration=5,
+                      blockindex=[list(range(d))], eps_scale=np.ones(d), γ=2.38) as s:
+        with pytest.raises(_lib.DemczError):
+            s.run()                                         # no archive yet
+        with pytest.raises(_lib.DemczError):
+            s.set_archive(np.zeros((1, d)))                 # < 2 rows: cannot draw r1 != r2
+        s.set_archive(np.zeros((3, d)))
+        with pytest.raises(_lib.DemczError):
+            s.run()                                         # archive smaller than N for last_N_of_Z init
+
+
+def test_streaming_rhat_matches_Rhat_gelman():
+    # the autostop Rhat comes from streaming accumulators in the step kernel; compare it with
+    # Rhat_gelman (src/utils.jl:2-20) evaluated by the oracle on the stored window
+    d, N, every = 5, 64, 50
+    mu, S = example_normpdf_target(d)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=10, Ngeneration=2 * every, blockindex=[list(range(d))],
+                      eps_scale=1e-5 * np.ones(d), γ=2.38, autostop=True, autostop_every=every, autostop_Rhat=0.0,
+                      seed=11) as s:
+        s.set_archive(_z0(200, d))
+        for w in range(2):
+            info = s.run(every)
+            assert info["rhat_valid"] and not info["stopped_by_rhat"]
+            chain, _ = s.get_chain()
+            ref = orc.rhat_gelman(chain[:, :, w * every:(w + 1) * every])
+            got = s.get_rhat()
+            np.testing.assert_allclose(got, ref, rtol=2e-4)
+            assert info["rhat_max"] == pytest.approx(got.max())
+
+
+def test_rhat_autostop_stops_and_odd_window():
+    d, N, every = 3, 128, 101            # odd window: n = floor(every/2), last generation of the window unused
+    mu, S = np.zeros(d), np.eye(d)
+    Z0 = np.random.default_rng(1).normal(size=(4 * N, d))
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=10, Ngeneration=20 * every, blockindex=[list(range(d))],
+                      eps_scale=1e-5 * np.ones(d), γ=2.38, autostop=True, autostop_every=every, autostop_Rhat=1.2,
+                      seed=13) as s:
+        s.set_archive(Z0)
+        info = s.run()
+        assert info["stopped_by_rhat"] and info["generations_total"] % every == 0
+        assert info["generations_total"] < 20 * every
+        chain, _ = s.get_chain()
+        g = info["generations_total"]
+        ref = orc.rhat_gelman(chain[:, :, g - every:g])
+        np.testing.assert_allclose(s.get_rhat(), ref, rtol=2e-4)
+        assert ref.max() < 1.2
+
+
+def test_adapt_gamma_follows_reference_rule():
+    # src/demcz_anneal.jl:48-57 replayed on the GPU's own log_obj history
+    d, N, G, every = 6, 96, 90, 15
+    mu = np.random.default_rng(4).random(d)
+    with DEMC.Sampler(DEMC.QuadraticLogobj(mu), d, N=N, K=10, Ngeneration=G, blockindex=[list(range(d))],
+                      eps_scale=1e-5 * np.ones(d), γ=2.38, anneal=True, T0=2.0, TN=1e-4, adapt=True, adapt_every=every,
+                      min_gamma=0.1, max_gamma=4.0, seed=21) as s:
+        s.set_archive(_z0(300, d))
+        info = s.run()
+        _, log_obj = s.get_chain()
+    gamma = 2.38
+    for w in range(G // every):
+        win = log_obj[:, w * every:(w + 1) * every]
+        ar = np.count_nonzero(np.diff(win, axis=1) != 0) / (N * every)
+        if ar < 0.1:
+            gamma = max(0.1, gamma / 2)
+        elif ar > 0.5:
+            gamma = min(4.0, 1.5 * gamma)
+    assert info["final_gamma"] == gamma
+
+
+def test_ring_buffer_archive_wraps():
+    d, N, K, G, cap = 4, 32, 2, 40, 200
+    mu, S = example_normpdf_target(d)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=K, Ngeneration=G, blockindex=[list(range(d))],
+                      eps_scale=1e-5 * np.ones(d), γ=2.38, archive_capacity=cap, trace=True, seed=2) as s:
+        s.set_archive(_z0(64, d))
+        s.run()
+        chain, _ = s.get_chain()
+        Z = s.get_archive()
+        tr = s.get_trace()
+    assert Z.shape == (cap, d)
+    total = 64 + N * (G // K)
+    assert total > cap
+    # logical order = oldest first; the newest N rows are the last append (generation G)
+    np.testing.assert_array_equal(Z[-N:], chain[:, :, G - 1])
+    np.testing.assert_array_equal(Z[-2 * N:-N], chain[:, :, G - 1 - K])
+    assert tr["r1"].max() < cap and tr["r2"].max() < cap and np.all(tr["r1"] != tr["r2"])
+
+
+def test_moments_api():
+    d, N = 5, 500
+    mu, S = example_normpdf_target(d)
+    X0 = np.random.default_rng(6).multivariate_normal(mu, S, size=N)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=10, Ngeneration=1, blockindex=[list(range(d))],
+                      eps_scale=np.ones(d), γ=2.38) as s:
+        s.set_archive(_z0(N, d))
+        s.set_state(X0)
+        m, c = s.get_moments()
+    X32 = X0.astype(np.float32).astype(np.float64)
+    np.testing.assert_allclose(m, X32.mean(axis=0), rtol=1e-10, atol=1e-12)
+    np.testing.assert_allclose(c, np.cov(X32.T, bias=True), rtol=1e-8, atol=1e-12)
