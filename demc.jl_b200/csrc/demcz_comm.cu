@@ -103,8 +103,8 @@ int demcz_comm_allgather_rows(demcz_ctx* c, int64_t phys_row0)
     if (c->o.world == 1) return DEMCZ_OK;
     if (phys_row0 + c->o.N_global > c->zcap)
         return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "multi-GPU append segment wraps the archive ring; raise archive_capacity");
-    float* seg = c->dZ + (size_t)phys_row0 * c->LD;
-    const size_t count = (size_t)c->o.N * c->LD;                 // floats per rank
+    float* seg = c->dZ + (size_t)phys_row0 * c->ZS;
+    const size_t count = (size_t)c->o.N * c->ZS;                 // floats per rank
     int rc = api().AllGather(seg + (size_t)c->o.rank * count, seg, count, ncclFloat32, (ncclComm_t)c->comm, c->stream);
     if (rc != ncclSuccess) return nccl_fail(c, "ncclAllGather", rc);
     return DEMCZ_OK;

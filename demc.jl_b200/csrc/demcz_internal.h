@@ -6,6 +6,7 @@
 #include <string>
 #include <vector>
 #include "../../include/demcz.h"
+#include "philox.cuh"
 
 enum { DEMCZ_LIK_NONE = -1, DEMCZ_LIK_MVN = 0, DEMCZ_LIK_LINREG = 1 };
 
@@ -19,7 +20,9 @@ struct demcz_ctx {
     cudaStream_t stream = nullptr;
     int LD = 0;          // archive row stride in floats (d rounded up to 4 -> 16-byte aligned rows)
     int ldx = 0;         // SoA leading dimension (N rounded up to 32)
-    int stages = 2;
+    int ZS = 0;          // archive row slot in floats (power of two >= LD for the closed-form path)
+    demcz::PhiloxKeys keys{};
+    float shift[32] = {0};
 
     int lik_kind = DEMCZ_LIK_NONE;
     std::vector<float> mvn_mu, mvn_W;   // W = L^-1, row-major d x d (lower)
@@ -43,6 +46,7 @@ struct demcz_ctx {
     double* dS2 = nullptr;
     float* dshift = nullptr;
     double* d_scratch = nullptr;
+    double* d_stage = nullptr;   // persistent FP64 staging for set_state/get_state: (N*d + N) doubles
 
     // run state
     int64_t g_done = 0;

@@ -65,7 +65,7 @@ __global__ void import_rows_kernel(const double* __restrict__ in, long long rows
 {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= rows) return;
-    for (int k = 0; k < LD; ++k) out[i * LD + k] = k < d ? (float)in[i + ldin * k] : 0.f;
+    for (int k = 0; k < LD; ++k) out[i * LD + k] = k < d ? (float)in[i + ldin * k] : 0.f;   // LD = row slot (floats)
 }
 
 __global__ void export_rows_kernel(const float* __restrict__ Z, long long rows, long long zstart, long long zcap,
@@ -208,19 +208,25 @@ MvnParams<LD> make_params(const demcz_ctx* c)
 {
     MvnParams<LD> P;
     memset(&P, 0, sizeof P);
-    for (int k = 0; k < c->o.d; ++k) P.mu[k] = c->mvn_mu[k];
-    for (int i = 0; i < c->o.d; ++i)
-        for (int j = 0; j <= i; ++j) P.W[i * (i + 1) / 2 + j] = c->mvn_W[(size_t)i * c->o.d + j];
+    const int d = c->o.d;
+    auto W = [&](int i, int j) { return (i < d && j < d && j <= i) ? c->mvn_W[(size_t)i * d + j] : 0.f; };
+    for (int k = 0; k < LD / 2; ++k)
+        P.mu2[k] = make_float2(2 * k < d ? c->mvn_mu[2 * k] : 0.f, 2 * k + 1 < d ? c->mvn_mu[2 * k + 1] : 0.f);
+    for (int i2 = 0; i2 < LD / 2; ++i2)
+        for (int j = 0; j < 2 * i2 + 2; ++j) P.Wp[i2 * (i2 + 1) + j] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
     P.c0 = c->mvn_c0;
     return P;
 }
 
-template <int LD, bool ACC, int STAGES>
+// resident blocks per SM the register allocation is held to (4 warps per block)
+template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
+
+template <int LD, bool ACC, bool FULL>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, kWarps, STAGES>;
-    const size_t smem = (size_t)kWarps * STAGES * SL::FLOATS * sizeof(float);
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>()>;
+    const size_t smem = (size_t)kWarps * 2 * SL::FLOATS * sizeof(float);
     static bool configured = false;       // per instantiation
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -236,23 +242,23 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 }
 
 template <int LD>
-cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc)
+cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
-    if (c->stages == 3) return acc ? launch_step_t<LD, true, 3>(c, a) : launch_step_t<LD, false, 3>(c, a);
-    return acc ? launch_step_t<LD, true, 2>(c, a) : launch_step_t<LD, false, 2>(c, a);
+    if (full) return acc ? launch_step_t<LD, true, true>(c, a) : launch_step_t<LD, false, true>(c, a);
+    return acc ? launch_step_t<LD, true, false>(c, a) : launch_step_t<LD, false, false>(c, a);
 }
 
-cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc)
+cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
     switch (c->LD) {
-        case 4:  return launch_step_ld<4>(c, a, acc);
-        case 8:  return launch_step_ld<8>(c, a, acc);
-        case 12: return launch_step_ld<12>(c, a, acc);
-        case 16: return launch_step_ld<16>(c, a, acc);
-        case 20: return launch_step_ld<20>(c, a, acc);
-        case 24: return launch_step_ld<24>(c, a, acc);
-        case 28: return launch_step_ld<28>(c, a, acc);
-        case 32: return launch_step_ld<32>(c, a, acc);
+        case 4:  return launch_step_ld<4>(c, a, acc, full);
+        case 8:  return launch_step_ld<8>(c, a, acc, full);
+        case 12: return launch_step_ld<12>(c, a, acc, full);
+        case 16: return launch_step_ld<16>(c, a, acc, full);
+        case 20: return launch_step_ld<20>(c, a, acc, full);
+        case 24: return launch_step_ld<24>(c, a, acc, full);
+        case 28: return launch_step_ld<28>(c, a, acc, full);
+        case 32: return launch_step_ld<32>(c, a, acc, full);
     }
     return cudaErrorInvalidValue;
 }
@@ -337,9 +343,10 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
     c->o.eps_scale = c->eps.data();
     c->gamma = o->gamma;
     c->LD = (o->d + 3) / 4 * 4;
+    c->ZS = o->d <= DEMCZ_MAX_DIM ? zslot(c->LD) : c->LD;
     c->ldx = (o->N + 31) / 32 * 32;
-    const char* st = getenv("DEMCZ_STAGES");
-    c->stages = (st && atoi(st) == 3) ? 3 : 2;
+    c->keys = make_philox_keys(o->seed);
+    if (const char* gr = getenv("DEMCZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));
     c->rhat.assign(o->d, NAN);
 
     auto bail = [&](int code) { demcz_destroy(c); return code; };
@@ -356,6 +363,7 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
     alloc((void**)&c->d_chain_changed, (size_t)c->ldx * sizeof(int));
     alloc((void**)&c->d_counters, 4 * sizeof(unsigned long long));
     alloc((void**)&c->d_scratch, (size_t)(8 * o->d + o->d * o->d + 16) * sizeof(double));
+    alloc((void**)&c->d_stage, ((size_t)o->N * o->d + o->N) * sizeof(double));
     if (o->autostop) {
         alloc((void**)&c->dS1[0], nx * sizeof(float));
         alloc((void**)&c->dS1[1], nx * sizeof(float));
@@ -395,7 +403,7 @@ extern "C" void demcz_destroy(demcz_ctx* c)
     demcz_linreg_free(c);
     void* ptrs[] = {c->dX, c->dlogp, c->dZ, c->dT, c->dhist, c->dlphist, c->tr_r1, c->tr_r2, c->tr_u, c->tr_xprop,
                     c->tr_lpprop, c->tr_acc, c->d_chain_changed, c->d_counters, c->dS1[0], c->dS1[1], c->dS2, c->dshift,
-                    c->d_scratch};
+                    c->d_scratch, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     if (c->ev_run[0]) { cudaEventDestroy(c->ev_run[0]); cudaEventDestroy(c->ev_run[1]); }
@@ -455,14 +463,14 @@ extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
     if (cap < M0) cap = M0;
     if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
     if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
-    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->LD * sizeof(float)));
+    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->ZS * sizeof(float)));
     c->zcap = cap;
     c->M = M0;
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, (size_t)M0 * o.d * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(stage, Z, (size_t)M0 * o.d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) {
-        import_rows_kernel<<<grid1d(M0), 256, 0, c->stream>>>(stage, M0, M0, o.d, c->LD, c->dZ);
+        import_rows_kernel<<<grid1d(M0), 256, 0, c->stream>>>(stage, M0, M0, o.d, c->ZS, c->dZ);
         e = cudaGetLastError();
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -491,23 +499,16 @@ extern "C" int demcz_set_state(demcz_ctx* c, const double* X, const double* logp
     CHECK_CTX(c);
     if (!X) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_state: X is null");
     const int N = c->o.N, d = c->o.d;
-    double* stage = nullptr;
-    CU(c, cudaMalloc((void**)&stage, ((size_t)N * d + N) * sizeof(double)));
-    cudaError_t e = cudaMemcpyAsync(stage, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-    if (e == cudaSuccess) {
-        import_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage, N, d, c->ldx, c->dX);
-        e = cudaGetLastError();
+    double* stage = c->d_stage;
+    CU(c, cudaMemcpyAsync(stage, X, (size_t)N * d * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    import_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage, N, d, c->ldx, c->dX);
+    CU(c, cudaGetLastError());
+    if (logp) {
+        CU(c, cudaMemcpyAsync(stage + (size_t)N * d, logp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+        f64_to_f32_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage + (size_t)N * d, N, c->dlogp);
+        CU(c, cudaGetLastError());
     }
-    if (e == cudaSuccess && logp) {
-        e = cudaMemcpyAsync(stage + (size_t)N * d, logp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream);
-        if (e == cudaSuccess) {
-            f64_to_f32_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage + (size_t)N * d, N, c->dlogp);
-            e = cudaGetLastError();
-        }
-    }
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(stage);
-    CU(c, e);
+    CU(c, cudaStreamSynchronize(c->stream));      // the caller's buffers are borrowed for the call only
     c->state_set = true;
     c->state_lp_valid = logp != nullptr;
     return DEMCZ_OK;
@@ -538,7 +539,7 @@ static int init_state_if_needed(demcz_ctx* c)
             if (c->M < o.N_global) return demcz_fail(c, DEMCZ_ERR_INVALID, "archive has %lld rows < N=%lld chains", (long long)c->M, (long long)o.N_global);
             if (c->M > c->zcap) return demcz_fail(c, DEMCZ_ERR_INVALID, "init from a wrapped archive is not supported");
             rows_to_soa_kernel<<<grid1d(o.N), 256, 0, c->stream>>>(c->dZ, c->M - o.N_global + o.chain_offset, c->zcap, o.N, o.d,
-                                                                   c->LD, c->ldx, c->dX);
+                                                                   c->ZS, c->ldx, c->dX);
             CU(c, cudaGetLastError());
         }
         c->state_set = true;
@@ -567,8 +568,14 @@ static int start_rhat_window(demcz_ctx* c)
     CU(c, cudaMemsetAsync(c->dS2, 0, (size_t)2 * o.d * sizeof(double), c->stream));
     CU(c, cudaMemsetAsync(c->d_scratch, 0, (size_t)o.d * sizeof(double), c->stream));
     colsum_kernel<<<dim3(std::min(grid1d(o.N), 64), o.d), 256, 0, c->stream>>>(c->dX, o.N, c->ldx, c->d_scratch);
-    shift_from_sums_kernel<<<1, 64, 0, c->stream>>>(c->d_scratch, o.d, 1.0 / o.N, c->dshift, nullptr);
     CU(c, cudaGetLastError());
+    // shift = this rank's population mean now: conditioning of the FP32 variance sums only (any value near
+    // the chains does).  The host needs it as a kernel parameter -> one small D2H per Rhat window.
+    double sums[64];
+    CU(c, cudaMemcpyAsync(sums, c->d_scratch, (size_t)o.d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 32; ++k) c->shift[k] = k < o.d ? (float)(sums[k] / o.N) : 0.f;
+    CU(c, cudaMemcpyAsync(c->dshift, c->shift, (size_t)o.d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     return DEMCZ_OK;
 }
 
@@ -659,7 +666,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.gen0 = o.gen_offset + g + 1;
             a.grel0 = g + 1;
             a.n_gens = n_gens;
-            a.key0 = (uint32_t)o.seed; a.key1 = (uint32_t)(o.seed >> 32);
+            a.keys = c->keys;
             a.nblocks = o.Nblocks;
             for (int b = 0; b < o.Nblocks; ++b) {
                 uint32_t mask = 0;
@@ -680,11 +687,12 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.accepted_total = c->d_counters + 1;
             a.run_skip_gi = (g == 0) ? 0 : -1;
             a.win_skip_gi = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : -1;
-            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; a.shift = c->dshift; }
+            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift, c->shift, sizeof a.shift); }
 
             if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
-            CU(c, launch_step(c, a, acc));
+            const bool full = o.Nblocks == 1 && a.blocks[0].mask == (o.d == 32 ? 0xFFFFFFFFu : ((1u << o.d) - 1u));
+            CU(c, launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
         }
@@ -795,16 +803,18 @@ extern "C" int demcz_get_state(demcz_ctx* c, double* X, double* logp)
     if (!c->state_set && !c->archive_set) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_state: no state and no archive");
     { int rc = init_state_if_needed(c); if (rc) return rc; }   // also evaluates logp after set_state(X, NULL)
     const int N = c->o.N, d = c->o.d;
-    double* stage = nullptr;
-    CU(c, cudaMalloc((void**)&stage, ((size_t)N * d + N) * sizeof(double)));
-    export_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dX, N, d, c->ldx, stage);
-    f32_to_f64_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dlogp, N, stage + (size_t)N * d);
-    cudaError_t e = cudaGetLastError();
-    if (e == cudaSuccess && X) e = cudaMemcpyAsync(X, stage, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess && logp) e = cudaMemcpyAsync(logp, stage + (size_t)N * d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-    cudaFree(stage);
-    CU(c, e);
+    double* stage = c->d_stage;
+    if (X) {
+        export_soa_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dX, N, d, c->ldx, stage);
+        CU(c, cudaGetLastError());
+        CU(c, cudaMemcpyAsync(X, stage, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    if (logp) {
+        f32_to_f64_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dlogp, N, stage + (size_t)N * d);
+        CU(c, cudaGetLastError());
+        CU(c, cudaMemcpyAsync(logp, stage + (size_t)N * d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    }
+    CU(c, cudaStreamSynchronize(c->stream));
     return DEMCZ_OK;
 }
 
@@ -818,7 +828,7 @@ extern "C" int demcz_get_archive(demcz_ctx* c, double* Z, int64_t* M)
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, (size_t)rows * c->o.d * sizeof(double)));
     const int64_t zstart = c->M > c->zcap ? c->M % c->zcap : 0;
-    export_rows_kernel<<<grid1d(rows), 256, 0, c->stream>>>(c->dZ, rows, zstart, c->zcap, c->o.d, c->LD, stage);
+    export_rows_kernel<<<grid1d(rows), 256, 0, c->stream>>>(c->dZ, rows, zstart, c->zcap, c->o.d, c->ZS, stage);
     cudaError_t e = cudaGetLastError();
     if (e == cudaSuccess) e = cudaMemcpyAsync(Z, stage, (size_t)rows * c->o.d * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);

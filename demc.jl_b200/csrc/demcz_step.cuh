@@ -21,7 +21,8 @@
 // same row with cp.async (LDGSTS, L2-only), so one warp instruction touches ~32/C rows instead
 // of 32 — the L1TEX wavefront count, not DRAM, is what a lane-per-row gather would saturate.
 // Rows are staged in shared memory (stride chosen conflict-free for LDS.128) and read back by
-// the owning lane.
+// the owning lane.  Archive rows sit in power-of-two slots (32/64/128 B) so that a row never
+// straddles a DRAM fetch atom.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -42,7 +43,7 @@ struct StepArgs {
     float* logp;
     int N, ldx, d;
     uint32_t chain_offset;       // global id of local chain 0
-    // archive: row-major, row stride LD floats (16-byte aligned rows)
+    // archive: row-major, row slot ZS floats (power of two; see zslot())
     const float* Z;
     uint32_t Mdraw;              // rows eligible for the draw
     uint32_t zstart, zcap;       // ring: physical row = (zstart + logical) mod zcap
@@ -50,7 +51,7 @@ struct StepArgs {
     long long gen0;              // absolute number (Philox counter) of the first generation
     long long grel0;             // 1-based number inside this context of the first generation
     int n_gens;
-    uint32_t key0, key1;
+    PhiloxKeys keys;             // the ten round keys of Philox4x32-10, precomputed on the host
     int nblocks;
     BlockDesc blocks[kMaxBlocks];
     float eps[32];
@@ -71,15 +72,49 @@ struct StepArgs {
     // split-Rhat accumulators of the current half-window
     float* S1;                   // [d][ldx]  sum_t (x - shift)
     double* S2;                  // [d]       sum_chains sum_t (x - shift)^2
-    const float* shift;          // [d]
+    float shift[32];             // population mean at the start of the window (conditioning only)
 };
 
+// Packed-FP32 (f32x2) arithmetic: one issue slot per two FMAs (SASS FFMA2 / FADD2 / FMUL2 on sm_100a).
+typedef unsigned long long u64;
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    u64 d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)), "l"(*reinterpret_cast<u64*>(&c)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    u64 d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fsub2(float2 a, float2 b)
+{
+    u64 d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    u64 d;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<u64*>(&a)), "l"(*reinterpret_cast<u64*>(&b)));
+    return *reinterpret_cast<float2*>(&d);
+}
+
+// Closed-form likelihood constants: W = L^-1 (Sigma = L L^T) stored as ROW PAIRS,
+//   Wp[i2*(i2+1) + j] = (W[2 i2][j], W[2 i2 + 1][j]),  j = 0 .. 2 i2 + 1
+// so that y_{2 i2}, y_{2 i2 + 1} accumulate together in one FFMA2 with dx_j broadcast.
 template <int LD>
 struct MvnParams {
-    float mu[LD];
-    float W[LD * (LD + 1) / 2];   // packed lower triangle (row-major) of L^-1, Sigma = L L^T
+    static constexpr int NWP = (LD / 2) * (LD / 2 + 1);
+    float2 Wp[NWP];
+    float2 mu2[LD / 2];
     float c0;
 };
+
+// archive row slot (floats) for a register width LD: next power of two, >= 8 floats (32-byte sector)
+__host__ __device__ constexpr int zslot(int LD) { return LD <= 8 ? 8 : LD <= 16 ? 16 : 32; }
 
 template <int LD>
 struct StageLayout {
@@ -87,6 +122,13 @@ struct StageLayout {
     static constexpr int LDS = (C % 2 == 1) ? LD : LD + 4;        // staged row stride (floats): odd #chunks
     static constexpr int ROWS = 64 * LDS;                         // 32 x r1 rows, 32 x r2 rows
     static constexpr int FLOATS = ROWS + 96;                      // + idx[64] + accept word[32]
+};
+
+// constants broadcast from shared memory: Wp | mu2 | eps2 | shift2   (float2 units)
+template <int LD>
+struct ConstLayout {
+    static constexpr int NWP = MvnParams<LD>::NWP;
+    static constexpr int MU = NWP, EPS = NWP + LD / 2, SHIFT = NWP + LD, TOTAL = NWP + 3 * LD / 2;
 };
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
@@ -106,33 +148,45 @@ __device__ __forceinline__ T warp_sum(T v)
     return v;
 }
 
-// log-density of the closed-form family: c0 - 0.5 |W (x - mu)|^2.  W, mu are kernel parameters
-// (constant bank), indices are compile-time -> every FFMA takes its matrix entry as a constant
-// operand, no loads.
+// log-density of the closed-form family: c0 - 0.5 |W (x - mu)|^2, constants from shared memory
+// (LDS.128 broadcasts), two rows of W per FFMA2.
 template <int LD>
-__device__ __forceinline__ float mvn_logdensity(const MvnParams<LD>& P, const float (&x)[LD])
+__device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ sc, float c0, const float2 (&x2)[LD / 2])
 {
+    using CL = ConstLayout<LD>;
     float dx[LD];
 #pragma unroll
-    for (int k = 0; k < LD; ++k) dx[k] = x[k] - P.mu[k];
-    float q = 0.f;
-#pragma unroll
-    for (int i = 0; i < LD; ++i) {
-        float y = 0.f;
-#pragma unroll
-        for (int j = 0; j <= i; ++j) y = fmaf(P.W[i * (i + 1) / 2 + j], dx[j], y);
-        q = fmaf(y, y, q);
+    for (int k2 = 0; k2 < LD / 2; k2 += 2) {
+        const float4 m = *reinterpret_cast<const float4*>(sc + CL::MU + k2);
+        const float2 a = fsub2(x2[k2], make_float2(m.x, m.y));
+        const float2 b = fsub2(x2[k2 + 1], make_float2(m.z, m.w));
+        dx[2 * k2] = a.x; dx[2 * k2 + 1] = a.y; dx[2 * k2 + 2] = b.x; dx[2 * k2 + 3] = b.y;
     }
-    return fmaf(-0.5f, q, P.c0);
+    float2 q2 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i2 = 0; i2 < LD / 2; ++i2) {
+        float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < 2 * i2 + 2; j += 2) {
+            const float4 w = *reinterpret_cast<const float4*>(sc + i2 * (i2 + 1) + j);
+            y = ffma2(make_float2(w.x, w.y), make_float2(dx[j], dx[j]), y);
+            y = ffma2(make_float2(w.z, w.w), make_float2(dx[j + 1], dx[j + 1]), y);
+        }
+        q2 = ffma2(y, y, q2);
+    }
+    return fmaf(-0.5f, q2.x + q2.y, c0);
 }
 
-template <int LD, bool ACC, int WARPS, int STAGES>
-__global__ void __launch_bounds__(WARPS * 32)
+// FULL: a single block covering every column (the common case) — no per-column masks.
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB>
+__global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
     using SL = StageLayout<LD>;
-    constexpr int C = SL::C, LDS = SL::LDS;
+    using CL = ConstLayout<LD>;
+    constexpr int C = SL::C, LDS = SL::LDS, ZS = zslot(LD), CP = ZS / 4, RPI = 32 / CP, STAGES = 2, H = LD / 2;
     extern __shared__ __align__(16) float smem[];
+    __shared__ __align__(16) float2 sc[CL::TOTAL];
     __shared__ unsigned int red_cnt[2];
     __shared__ float red_s2[ACC ? LD : 1];
 
@@ -145,34 +199,47 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
 
     if (threadIdx.x < 2) red_cnt[threadIdx.x] = 0u;
     if (ACC && threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
+    for (int t = threadIdx.x; t < CL::NWP + H; t += WARPS * 32) sc[t] = t < CL::NWP ? P.Wp[t] : P.mu2[t - CL::NWP];
+    if (threadIdx.x < H) {
+        sc[CL::EPS + threadIdx.x] = make_float2(a.eps[2 * threadIdx.x], a.eps[2 * threadIdx.x + 1]);
+        sc[CL::SHIFT + threadIdx.x] = make_float2(a.shift[2 * threadIdx.x], a.shift[2 * threadIdx.x + 1]);
+    }
+    __syncthreads();
 
-    float x[LD];
+    float2 x2[H];
 #pragma unroll
-    for (int k = 0; k < LD; ++k) x[k] = (k < a.d) ? a.X[(size_t)k * a.ldx + cl] : 0.f;
+    for (int k = 0; k < H; ++k) {
+        x2[k].x = (2 * k < a.d) ? a.X[(size_t)(2 * k) * a.ldx + cl] : 0.f;
+        x2[k].y = (2 * k + 1 < a.d) ? a.X[(size_t)(2 * k + 1) * a.ldx + cl] : 0.f;
+    }
     float lp = a.logp[cl];
 
-    float s1[ACC ? LD : 1], s2[ACC ? LD : 1], sh[ACC ? LD : 1];
+    float2 s1[ACC ? H : 1], s2[ACC ? H : 1];
     if (ACC) {
 #pragma unroll
-        for (int k = 0; k < LD; ++k) {
-            sh[k] = (k < a.d) ? a.shift[k] : 0.f;
-            s1[k] = (k < a.d) ? a.S1[(size_t)k * a.ldx + cl] : 0.f;
-            s2[k] = 0.f;
+        for (int k = 0; k < H; ++k) {
+            s1[k].x = (2 * k < a.d) ? a.S1[(size_t)(2 * k) * a.ldx + cl] : 0.f;
+            s1[k].y = (2 * k + 1 < a.d) ? a.S1[(size_t)(2 * k + 1) * a.ldx + cl] : 0.f;
+            s2[k] = make_float2(0.f, 0.f);
         }
     }
 
-    const int nb = a.nblocks;
+    const int nb = FULL ? 1 : a.nblocks;
     const int Q = a.n_gens * nb;
     int cnt_run = 0, cnt_win = 0, cnt_acc = 0;
 
     // ---- producer side of the per-warp pipeline -------------------------------------------
+    // lane -> (row within a group of RPI rows, 16-byte piece of the row slot): lane-only, so the
+    // copy loop below has compile-time shared-memory offsets
+    const int lrow = lane / CP, lpiece = lane % CP;
+    const bool pact = lpiece < C;
+    const int soff = lrow * LDS + lpiece * 4;
     int pg = 0, pb = 0;
     auto prefetch = [&](int stage) {
         float* st = wbase + stage * SL::FLOATS;
         uint32_t* idx = reinterpret_cast<uint32_t*>(st + SL::ROWS);
         const long long g = a.gen0 + pg;
-        const u32x4 w = philox4x32_10(cid, (uint32_t)g, (uint32_t)pb << 16, (uint32_t)((unsigned long long)g >> 32),
-                                      a.key0, a.key1);
+        const u32x4 w = philox4x32_10(cid, (uint32_t)g, (uint32_t)pb << 16, (uint32_t)((unsigned long long)g >> 32), a.keys);
         uint32_t r1, r2;
         draw_pair(w.x, w.y, a.Mdraw, r1, r2);
         r1 += a.zstart; if (r1 >= a.zcap) r1 -= a.zcap;
@@ -181,72 +248,74 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         idx[32 + lane] = r2;
         idx[64 + lane] = w.z;
         __syncwarp();
+        const float* zb = a.Z + lpiece * 4;
 #pragma unroll
-        for (int it = 0; it < 2 * C; ++it) {
-            const int chunk = it * 32 + lane;
-            const int row = chunk / C;
-            const int piece = chunk - row * C;
-            cp_async16(st + row * LDS + piece * 4, a.Z + (size_t)idx[row] * LD + piece * 4);
+        for (int it = 0; it < 64 / RPI; ++it) {
+            const uint32_t row = idx[it * RPI + lrow];
+            if (pact) cp_async16(st + it * RPI * LDS + soff, zb + (size_t)row * ZS);
         }
-        if (++pb == nb) { pb = 0; ++pg; }
+        if (!FULL) { if (++pb == nb) { pb = 0; ++pg; } } else { ++pg; }
     };
 
-#pragma unroll
-    for (int s = 0; s < STAGES - 1; ++s) {
-        if (s < Q) prefetch(s);
-        cp_async_commit();
-    }
+    if (0 < Q) prefetch(0);
+    cp_async_commit();
 
     // ---- consumer ---------------------------------------------------------------------------
     int cg = 0, cb = 0;
     float lp_gen0 = lp;
     for (int q = 0; q < Q; ++q) {
-        if (q + STAGES - 1 < Q) prefetch((q + STAGES - 1) % STAGES);
+        if (q + 1 < Q) prefetch((q + 1) & 1);
         cp_async_commit();                       // (possibly empty) keeps the group count uniform
-        cp_async_wait<STAGES - 1>();
+        cp_async_wait<1>();
         __syncwarp();
 
-        const float* st = wbase + (q % STAGES) * SL::FLOATS;
+        const float* st = wbase + (q & 1) * SL::FLOATS;
         const uint32_t* idx = reinterpret_cast<const uint32_t*>(st + SL::ROWS);
-        const BlockDesc bd = a.blocks[cb];
         const long long g = a.gen0 + cg;
         const long long grel = a.grel0 + cg;
+        const uint32_t g_lo = (uint32_t)g, g_hi = (uint32_t)((unsigned long long)g >> 32);
+        const uint32_t mask = FULL ? 0xFFFFFFFFu : a.blocks[cb].mask;
+        const float cs = FULL ? a.blocks[0].cscale : a.blocks[cb].cscale;
+        const float2 cs2 = make_float2(cs, cs);
 
-        float dz[LD];
+        // x' = x + c (Z[r1] - Z[r2]) + eps .* z
+        float2 xp[H];
         {
             const float4* ra = reinterpret_cast<const float4*>(st + lane * LDS);
             const float4* rb = reinterpret_cast<const float4*>(st + (32 + lane) * LDS);
 #pragma unroll
             for (int c = 0; c < C; ++c) {
                 const float4 A = ra[c], B = rb[c];
-                dz[4 * c + 0] = A.x - B.x; dz[4 * c + 1] = A.y - B.y;
-                dz[4 * c + 2] = A.z - B.z; dz[4 * c + 3] = A.w - B.w;
+                xp[2 * c] = fsub2(make_float2(A.x, A.y), make_float2(B.x, B.y));
+                xp[2 * c + 1] = fsub2(make_float2(A.z, A.w), make_float2(B.z, B.w));
             }
         }
         const uint32_t wacc = idx[64 + lane];
-
-        float xp[LD];
 #pragma unroll
-        for (int q4 = 0; q4 < C; ++q4) {
-            if ((bd.mask >> (4 * q4)) & 0xFu) {      // warp-uniform
-                const u32x4 wn = philox4x32_10(cid, (uint32_t)g, ((uint32_t)cb << 16) | (uint32_t)(1 + q4),
-                                               (uint32_t)((unsigned long long)g >> 32), a.key0, a.key1);
-                float z[4];
-                box_muller(wn.x, wn.y, z[0], z[1]);
-                box_muller(wn.z, wn.w, z[2], z[3]);
+        for (int q8 = 0; q8 < (LD + 7) / 8; ++q8) {
+            if (FULL || ((mask >> (8 * q8)) & 0xFFu)) {      // warp-uniform
+                const u32x4 wn = philox4x32_10(cid, g_lo, ((uint32_t)cb << 16) | (uint32_t)(1 + q8), g_hi, a.keys);
+                const uint32_t ww[4] = {wn.x, wn.y, wn.z, wn.w};
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int k = 4 * q4 + j;
-                    const float diff = fmaf(a.eps[k], z[j], bd.cscale * dz[k]);
-                    xp[k] = ((bd.mask >> k) & 1u) ? x[k] + diff : x[k];
+                for (int j = 0; j < 4; j += 2) {
+                    const int k2 = 4 * q8 + j;               // column pair index
+                    if (k2 < H) {
+                        const float4 e = *reinterpret_cast<const float4*>(sc + CL::EPS + k2);
+                        xp[k2] = ffma2(cs2, xp[k2], ffma2(make_float2(e.x, e.y), box_muller16(ww[j]), x2[k2]));
+                        xp[k2 + 1] = ffma2(cs2, xp[k2 + 1], ffma2(make_float2(e.z, e.w), box_muller16(ww[j + 1]), x2[k2 + 1]));
+                    }
                 }
-            } else {
+            }
+        }
+        if (!FULL) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xp[4 * q4 + j] = x[4 * q4 + j];
+            for (int k = 0; k < H; ++k) {
+                xp[k].x = ((mask >> (2 * k)) & 1u) ? xp[k].x : x2[k].x;
+                xp[k].y = ((mask >> (2 * k + 1)) & 1u) ? xp[k].y : x2[k].y;
             }
         }
 
-        const float lpp = mvn_logdensity<LD>(P, xp);
+        const float lpp = mvn_logdensity<LD>(sc, P.c0, xp);
         const float u = uniform01(wacc);
         const float logu = __logf(u);
         const float delta = lpp - lp;
@@ -262,16 +331,16 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             a.tr_r1[o] = l1; a.tr_r2[o] = l2; a.tr_u[o] = u; a.tr_lpprop[o] = lpp; a.tr_acc[o] = acc ? 1 : 0;
 #pragma unroll
             for (int k = 0; k < LD; ++k)
-                if (k < a.d) a.tr_xprop[(((size_t)(grel - 1) * nb + cb) * a.d + k) * a.N + chain] = xp[k];
+                if (k < a.d) a.tr_xprop[(((size_t)(grel - 1) * nb + cb) * a.d + k) * a.N + chain] = (k & 1) ? xp[k / 2].y : xp[k / 2].x;
         }
 
 #pragma unroll
-        for (int k = 0; k < LD; ++k) x[k] = acc ? xp[k] : x[k];
+        for (int k = 0; k < H; ++k) { x2[k].x = acc ? xp[k].x : x2[k].x; x2[k].y = acc ? xp[k].y : x2[k].y; }
         lp = acc ? lpp : lp;
         cnt_acc += (acc && active) ? 1 : 0;
-        __syncwarp();                            // stage q%STAGES is free for the next prefetch
+        __syncwarp();                            // stage q&1 is free for the next prefetch
 
-        if (++cb == nb) {                        // end of generation: runchain! bookkeeping (src/demcz.jl:84-87)
+        if (FULL || ++cb == nb) {                // end of generation: runchain! bookkeeping (src/demcz.jl:84-87)
             cb = 0;
             const bool changed = active && (lp != lp_gen0);
             cnt_run += (changed && cg != a.run_skip_gi) ? 1 : 0;
@@ -279,15 +348,17 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             if (a.hist && active) {
 #pragma unroll
                 for (int k = 0; k < LD; ++k)
-                    if (k < a.d) a.hist[((size_t)(grel - 1) * a.d + k) * a.N + chain] = x[k];
+                    if (k < a.d) a.hist[((size_t)(grel - 1) * a.d + k) * a.N + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
                 a.lphist[(size_t)(grel - 1) * a.N + chain] = lp;
             }
             if (ACC) {
 #pragma unroll
-                for (int k = 0; k < LD; ++k) {
-                    const float t = x[k] - sh[k];
-                    s1[k] += t;
-                    s2[k] = fmaf(t, t, s2[k]);
+                for (int k = 0; k < H; k += 2) {
+                    const float4 sh = *reinterpret_cast<const float4*>(sc + CL::SHIFT + k);
+                    const float2 t0 = fsub2(x2[k], make_float2(sh.x, sh.y));
+                    const float2 t1 = fsub2(x2[k + 1], make_float2(sh.z, sh.w));
+                    s1[k] = fadd2(s1[k], t0);         s1[k + 1] = fadd2(s1[k + 1], t1);
+                    s2[k] = ffma2(t0, t0, s2[k]);     s2[k + 1] = ffma2(t1, t1, s2[k + 1]);
                 }
             }
             lp_gen0 = lp;
@@ -299,20 +370,20 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     if (active) {
 #pragma unroll
         for (int k = 0; k < LD; ++k)
-            if (k < a.d) a.X[(size_t)k * a.ldx + chain] = x[k];
+            if (k < a.d) a.X[(size_t)k * a.ldx + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
         a.logp[chain] = lp;
         if (a.chain_changed) a.chain_changed[chain] += cnt_run;
         if (a.Zw) {                              // Zmat[M+1,:] .= Xcurrent[ic,:]  (src/demcz.jl:88-91)
             uint32_t row = a.append_row0 + a.chain_offset + (uint32_t)chain;
             if (row >= a.zcap) row -= a.zcap;
-            float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * LD);
+            float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * ZS);
 #pragma unroll
-            for (int c = 0; c < C; ++c) dst[c] = make_float4(x[4 * c], x[4 * c + 1], x[4 * c + 2], x[4 * c + 3]);
+            for (int c = 0; c < C; ++c) dst[c] = make_float4(x2[2 * c].x, x2[2 * c].y, x2[2 * c + 1].x, x2[2 * c + 1].y);
         }
         if (ACC) {
 #pragma unroll
             for (int k = 0; k < LD; ++k)
-                if (k < a.d) a.S1[(size_t)k * a.ldx + chain] = s1[k];
+                if (k < a.d) a.S1[(size_t)k * a.ldx + chain] = (k & 1) ? s1[k / 2].y : s1[k / 2].x;
         }
     }
     __syncthreads();                             // red_* initialised
@@ -322,7 +393,7 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         if (ACC) {
 #pragma unroll
             for (int k = 0; k < LD; ++k) {
-                const float v = warp_sum(active ? s2[k] : 0.f);
+                const float v = warp_sum(active ? ((k & 1) ? s2[k / 2].y : s2[k / 2].x) : 0.f);
                 if (lane == 0) atomicAdd(&red_s2[k], v);
             }
         }
@@ -340,12 +411,19 @@ template <int LD>
 __global__ void mvn_eval_kernel(const float* __restrict__ X, int n, int ldx, int d, float* __restrict__ out,
                                 const __grid_constant__ MvnParams<LD> P)
 {
+    using CL = ConstLayout<LD>;
+    __shared__ __align__(16) float2 sc[CL::TOTAL];
+    for (int t = threadIdx.x; t < CL::NWP + LD / 2; t += blockDim.x) sc[t] = t < CL::NWP ? P.Wp[t] : P.mu2[t - CL::NWP];
+    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float x[LD];
+    float2 x2[LD / 2];
 #pragma unroll
-    for (int k = 0; k < LD; ++k) x[k] = (k < d) ? X[(size_t)k * ldx + i] : 0.f;
-    out[i] = mvn_logdensity<LD>(P, x);
+    for (int k = 0; k < LD / 2; ++k) {
+        x2[k].x = (2 * k < d) ? X[(size_t)(2 * k) * ldx + i] : 0.f;
+        x2[k].y = (2 * k + 1 < d) ? X[(size_t)(2 * k + 1) * ldx + i] : 0.f;
+    }
+    out[i] = mvn_logdensity<LD>(sc, P.c0, x2);
 }
 
 }  // namespace demcz

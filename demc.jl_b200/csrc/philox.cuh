@@ -2,7 +2,8 @@
 // Stream layout (shared bit-for-bit with oracle/demcz_oracle.c):
 //   key = (seed_lo, seed_hi);  ctr = (global chain id, gen lo32, (block << 16) | call, gen hi32)
 //   call 0     -> (w_r1, w_r2, w_accept, spare)
-//   call 1 + q -> jitter normals of columns 4q..4q+3 (two Box-Muller pairs)
+//   call 1 + q -> jitter normals of columns 8q..8q+7: word j -> one Box-Muller pair (16-bit
+//                 uniforms from the high / low half-word) -> columns 8q+2j, 8q+2j+1
 // Replaces the global MersenneTwister draws of src/demcz.jl:177,179,184,186,198 (reference).
 #pragma once
 #include <stdint.h>
@@ -14,19 +15,28 @@ constexpr uint32_t kPhiloxW0 = 0x9E3779B9u, kPhiloxW1 = 0xBB67AE85u;
 
 struct u32x4 { uint32_t x, y, z, w; };
 
-__device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
-                                               uint32_t k0, uint32_t k1)
+// The key schedule (key + r * Weyl constant) depends only on the seed: the host expands it once and
+// the kernels take the ten round keys as constant-bank operands of the XORs.
+struct PhiloxKeys { uint32_t k0[10], k1[10]; };
+
+inline PhiloxKeys make_philox_keys(uint64_t seed)
+{
+    PhiloxKeys k;
+    uint32_t a = (uint32_t)seed, b = (uint32_t)(seed >> 32);
+    for (int r = 0; r < 10; ++r) { k.k0[r] = a; k.k1[r] = b; a += kPhiloxW0; b += kPhiloxW1; }
+    return k;
+}
+
+__device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K)
 {
 #pragma unroll
     for (int r = 0; r < 10; ++r) {
         const uint32_t hi0 = __umulhi(kPhiloxM0, c0), lo0 = kPhiloxM0 * c0;
         const uint32_t hi1 = __umulhi(kPhiloxM1, c2), lo1 = kPhiloxM1 * c2;
-        c0 = hi1 ^ c1 ^ k0;
+        c0 = hi1 ^ c1 ^ K.k0[r];
         c1 = lo1;
-        c2 = hi0 ^ c3 ^ k1;
+        c2 = hi0 ^ c3 ^ K.k1[r];
         c3 = lo0;
-        k0 += kPhiloxW0;   // uniform across the warp: folded into constants by the compiler
-        k1 += kPhiloxW1;
     }
     return u32x4{c0, c1, c2, c3};
 }
@@ -45,16 +55,21 @@ __device__ __forceinline__ void draw_pair(uint32_t w1, uint32_t w2, uint32_t M, 
     r2 = j + (j >= r1 ? 1u : 0u);
 }
 
-// z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln u1).  The angle is folded to
-// (-pi, pi) (cos/sin(t + pi) = -cos/-sin t) where the MUFU approximations are most accurate.
-__device__ __forceinline__ void box_muller(uint32_t wa, uint32_t wb, float& z0, float& z1)
+// One Philox word -> two N(0,1) draws (the eps jitter of src/demcz.jl:184/186):
+//   u1 = ((w >> 16) + 0.5) 2^-16, u2 = ((w & 0xffff) + 0.5) 2^-16   (exact in FP32, in (0,1))
+//   z0 = r cos(2 pi u2), z1 = r sin(2 pi u2), r = sqrt(-2 ln u1)
+// The angle is folded to (-pi, pi) (cos/sin(t + pi) = -cos/-sin t) where the MUFU approximations
+// are most accurate.
+__device__ __forceinline__ float2 box_muller16(uint32_t w)
 {
-    const float u1 = uniform01(wa), u2 = uniform01(wb);
-    const float r = sqrtf(-2.0f * __logf(u1));
-    float s, c;
-    __sincosf(6.2831853071795864769f * (u2 - 0.5f), &s, &c);
-    z0 = -r * c;
-    z1 = -r * s;
+    const float u1 = fmaf((float)(w >> 16), 1.52587890625e-05f, 7.62939453125e-06f);
+    const float t = fmaf((float)(w & 0xFFFFu), 1.52587890625e-05f, 7.62939453125e-06f - 0.5f);   // u2 - 1/2
+    float l2, r, s, c;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(u1));
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(-1.3862943611198906f * l2));               // sqrt(-2 ln u1)
+    asm("sin.approx.ftz.f32 %0, %1;" : "=f"(s) : "f"(6.2831853071795864769f * t));
+    asm("cos.approx.ftz.f32 %0, %1;" : "=f"(c) : "f"(6.2831853071795864769f * t));
+    return make_float2(-r * c, -r * s);
 }
 
 }  // namespace demcz

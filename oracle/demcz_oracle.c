@@ -52,10 +52,11 @@ void orc_draw_pair(uint32_t w_r1, uint32_t w_r2, uint32_t M, uint32_t* r1, uint3
     *r2 = j + (j >= a ? 1u : 0u);
 }
 
-/* randn() of src/demcz.jl:184,186 replaced by Box-Muller on two Philox words */
-void orc_box_muller(uint32_t wa, uint32_t wb, double* z0, double* z1)
+/* randn() of src/demcz.jl:184,186 replaced by Box-Muller on ONE Philox word: 16-bit uniforms from the
+ * high / low half-word, u = (h + 0.5) 2^-16 (exact in FP32, in (0,1)) */
+void orc_box_muller16(uint32_t w, double* z0, double* z1)
 {
-    double u1 = orc_uniform(wa), u2 = orc_uniform(wb);
+    double u1 = ((double)(w >> 16) + 0.5) * (1.0 / 65536.0), u2 = ((double)(w & 0xFFFFu) + 0.5) * (1.0 / 65536.0);
     double r = sqrt(-2.0 * log(u1));
     double th = 6.283185307179586476925286766559 * u2;
     *z0 = r * cos(th);
@@ -163,21 +164,20 @@ static void chain_generation(const orc_opts* o, const orc_lik* lik, int ic, doub
         /* γ*(…) if blocklen == 1 else γ/sqrt(2*blocklen)*(…)  :183-187 */
         const double c = blocklen == 1 ? o->gamma : o->gamma / sqrt(2.0 * blocklen);
         for (int k = 0; k < d; ++k) xp[k] = x[k];                 /* de_diffvec = zeros  :180 */
-        int have_q = -1; double zn[4] = {0, 0, 0, 0};
+        int have_q = -1; double zn[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         for (int t = b0; t < b1; ++t) {
             const int k = o->block_idx[t];
-            const int q = k >> 2;
+            const int q = k >> 3;
             if (q != have_q) {                                    /* randn(blocklen)  :186 */
                 uint32_t cn[4] = { cid, (uint32_t)gen_abs, ((uint32_t)ib << 16) | (uint32_t)(1 + q),
                                    (uint32_t)((uint64_t)gen_abs >> 32) };
                 uint32_t wn[4];
                 orc_philox4x32_10(cn, key, wn);
-                orc_box_muller(wn[0], wn[1], &zn[0], &zn[1]);
-                orc_box_muller(wn[2], wn[3], &zn[2], &zn[3]);
+                for (int j = 0; j < 4; ++j) orc_box_muller16(wn[j], &zn[2 * j], &zn[2 * j + 1]);   /* columns 8q..8q+7 */
                 have_q = q;
             }
             const double diff = c * (ZAT(Z, Zld, d, o->z_rowmajor, r1, k) - ZAT(Z, Zld, d, o->z_rowmajor, r2, k))
-                              + o->eps_scale[k] * zn[k & 3];
+                              + o->eps_scale[k] * zn[k & 7];
             xp[k] = x[k] + diff;                                  /* Xproposal = Xcurrent .+ de_diffvec :188 */
         }
         const double lpp = orc_logdensity(lik, xp);              /* logobj(Xproposal)  :189 */

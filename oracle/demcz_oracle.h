@@ -31,13 +31,13 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
  *   key = (seed_lo, seed_hi)
  *   ctr = (global chain id, gen_abs lo32, (block << 16) | call, gen_abs hi32)
  *   call 0      -> words (w_r1, w_r2, w_accept, spare)
- *   call 1 + q  -> 4 words -> 2 Box-Muller pairs -> jitter normals of columns 4q..4q+3
+ *   call 1 + q  -> 4 words -> 4 Box-Muller pairs (16-bit uniforms) -> jitter normals of columns 8q..8q+7
  * uniform(w)  = ((w >> 9) + 0.5) * 2^-23          (exact in FP32 and FP64, in (0,1))
  * r1 = mulhi32(w_r1, M); j = mulhi32(w_r2, M-1); r2 = j + (j >= r1)   (0-based; Q9)
  */
 double orc_uniform(uint32_t w);
 void orc_draw_pair(uint32_t w_r1, uint32_t w_r2, uint32_t M, uint32_t* r1, uint32_t* r2);
-void orc_box_muller(uint32_t wa, uint32_t wb, double* z0, double* z1);
+void orc_box_muller16(uint32_t w, double* z0, double* z1);
 
 /* ---- likelihood descriptors (the reference passes a closure: src/demcz.jl:189) ------------- */
 enum { ORC_LIK_MVNORMAL = 0, ORC_LIK_LINREG = 1 };

@@ -60,8 +60,12 @@ def draw_pair(w_r1, w_r2, M):
     return a.astype(np.int64), (j + (j >= a)).astype(np.int64)
 
 
-def box_muller(wa, wb):
-    u1, u2 = uniform(wa), uniform(wb)
+def box_muller16(w):
+    """One Philox word -> two N(0,1) draws (replaces randn of src/demcz.jl:184,186): 16-bit uniforms from the
+    high / low half-word, u = (h + 0.5) 2^-16 (exact in FP32, in (0,1)); z0 = r cos(2 pi u2), z1 = r sin(2 pi u2)."""
+    w = np.asarray(w, dtype=np.uint32)
+    u1 = ((w >> np.uint32(16)).astype(np.float64) + 0.5) / 65536.0
+    u2 = ((w & np.uint32(0xFFFF)).astype(np.float64) + 0.5) / 65536.0
     r = np.sqrt(-2.0 * np.log(u1))
     th = 2.0 * math.pi * u2
     return r * np.cos(th), r * np.sin(th)
@@ -143,13 +147,11 @@ def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T
     zn = {}
     Xp = X.copy()                                                          # de_diffvec = zeros :180
     for k in block:
-        q = int(k) >> 2
+        q = int(k) >> 3
         if q not in zn:                                                    # randn(blocklen) :186
             wn = philox4x32_10(counters(cid, gen_abs, ib, 1 + q), key)
-            z0, z1 = box_muller(wn[:, 0], wn[:, 1])
-            z2, z3 = box_muller(wn[:, 2], wn[:, 3])
-            zn[q] = (z0, z1, z2, z3)
-        diff = c * (Z[r1, k] - Z[r2, k]) + eps_scale[k] * zn[q][int(k) & 3]
+            zn[q] = [z for j in range(4) for z in box_muller16(wn[:, j])]   # columns 8q .. 8q+7
+        diff = c * (Z[r1, k] - Z[r2, k]) + eps_scale[k] * zn[q][int(k) & 7]
         Xp[:, k] = X[:, k] + diff                                          # :188
     lpp = lik.logdensity(Xp)                                               # :189
     u = uniform(w[:, 2])
