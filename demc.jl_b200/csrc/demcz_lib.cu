@@ -203,17 +203,26 @@ namespace {
 
 constexpr int kWarps = 4;
 
+// production structure of the step kernel (see tools/step_tune.cu and profiles/ for how it was chosen)
+constexpr int kStepOpt = DEMCZ_STEP_OPT;
+
 template <int LD>
-MvnParams<LD> make_params(const demcz_ctx* c)
+MvnParams<LD> make_params(const demcz_ctx* c, bool jmajor)
 {
+    using MP = MvnParams<LD>;
     MvnParams<LD> P;
     memset(&P, 0, sizeof P);
     const int d = c->o.d;
     auto W = [&](int i, int j) { return (i < d && j < d && j <= i) ? c->mvn_W[(size_t)i * d + j] : 0.f; };
     for (int k = 0; k < LD / 2; ++k)
         P.mu2[k] = make_float2(2 * k < d ? c->mvn_mu[2 * k] : 0.f, 2 * k + 1 < d ? c->mvn_mu[2 * k + 1] : 0.f);
-    for (int i2 = 0; i2 < LD / 2; ++i2)
-        for (int j = 0; j < 2 * i2 + 2; ++j) P.Wp[i2 * (i2 + 1) + j] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
+    if (jmajor) {
+        for (int j = 0; j < LD; ++j)
+            for (int i2 = j / 2; i2 < LD / 2; ++i2) P.W[MP::wj_off(j) + i2 - j / 2] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
+    } else {
+        for (int i2 = 0; i2 < LD / 2; ++i2)
+            for (int j = 0; j < 2 * i2 + 2; ++j) P.W[i2 * (i2 + 1) + j] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
+    }
     P.c0 = c->mvn_c0;
     return P;
 }
@@ -225,7 +234,7 @@ template <int LD, bool ACC, bool FULL>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>()>;
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt>;
     const size_t smem = (size_t)kWarps * 2 * SL::FLOATS * sizeof(float);
     static bool configured = false;       // per instantiation
     if (!configured) {
@@ -236,7 +245,7 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     }
     const int threads = kWarps * 32;
     const int grid = (a.N + threads - 1) / threads;
-    const MvnParams<LD> P = make_params<LD>(c);
+    const MvnParams<LD> P = make_params<LD>(c, kStepOpt & OPT_JMAJOR);
     kern<<<grid, threads, smem, c->stream>>>(a, P);
     return cudaGetLastError();
 }
@@ -266,7 +275,7 @@ cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 template <int LD>
 cudaError_t launch_eval_t(demcz_ctx* c, const float* X, int n, int ldx, float* out)
 {
-    const MvnParams<LD> P = make_params<LD>(c);
+    const MvnParams<LD> P = make_params<LD>(c, false);
     mvn_eval_kernel<LD><<<(n + 127) / 128, 128, 0, c->stream>>>(X, n, ldx, c->o.d, out, P);
     return cudaGetLastError();
 }
@@ -675,7 +684,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
                 a.blocks[b].mask = mask;
                 a.blocks[b].cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
             }
-            for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
+            for (int k = 0; k < o.d; ++k) (&a.eps2[0].x)[k] = (float)c->eps[k];
             a.Ttab = o.anneal ? c->dT : nullptr;
             a.Zw = append ? c->dZ : nullptr;
             a.append_row0 = (uint32_t)(c->M % c->zcap);
@@ -687,7 +696,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.accepted_total = c->d_counters + 1;
             a.run_skip_gi = (g == 0) ? 0 : -1;
             a.win_skip_gi = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : -1;
-            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift, c->shift, sizeof a.shift); }
+            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift2, c->shift, sizeof a.shift2); }
 
             if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));

@@ -54,7 +54,7 @@ struct StepArgs {
     PhiloxKeys keys;             // the ten round keys of Philox4x32-10, precomputed on the host
     int nblocks;
     BlockDesc blocks[kMaxBlocks];
-    float eps[32];
+    float2 eps2[16];             // eps_scale as column pairs
     const float* Ttab;           // temperatures, indexed by grel-1; nullptr -> plain accept
     // append (only when the last generation of the launch is a multiple of K)
     float* Zw;                   // archive base for the append, nullptr -> no append
@@ -72,7 +72,7 @@ struct StepArgs {
     // split-Rhat accumulators of the current half-window
     float* S1;                   // [d][ldx]  sum_t (x - shift)
     double* S2;                  // [d]       sum_chains sum_t (x - shift)^2
-    float shift[32];             // population mean at the start of the window (conditioning only)
+    float2 shift2[16];           // population mean at the start of the window (conditioning only), column pairs
 };
 
 // Packed-FP32 (f32x2) arithmetic: one issue slot per two FMAs (SASS FFMA2 / FADD2 / FMUL2 on sm_100a).
@@ -102,14 +102,29 @@ __device__ __forceinline__ float2 fmul2(float2 a, float2 b)
     return *reinterpret_cast<float2*>(&d);
 }
 
-// Closed-form likelihood constants: W = L^-1 (Sigma = L L^T) stored as ROW PAIRS,
-//   Wp[i2*(i2+1) + j] = (W[2 i2][j], W[2 i2 + 1][j]),  j = 0 .. 2 i2 + 1
+// Kernel-structure switches (compile time; tools/step_tune.cu times the combinations on the GPU):
+enum : int {
+    OPT_W_SMEM = 1,    // W / mu broadcast from shared memory (LDS.128) instead of the constant bank (LDCU -> uniform regs)
+    OPT_JMAJOR = 2,    // quadratic form walks W column by column with LD/2 independent accumulators (ILP) instead of row pairs
+    OPT_IDX_VEC = 4,   // gather: each lane copies pieces of consecutive staged rows (LDS.128 index reads, predicated LDGSTS)
+    OPT_S2_SMEM = 8,   // Rhat sum-of-squares accumulators live in shared memory instead of registers
+    OPT_ABL_NOJIT = 16, OPT_ABL_NOQUAD = 32   // ablations for tools/step_tune.cu only (wrong results)
+};
+
+// Closed-form likelihood constants: W = L^-1 (Sigma = L L^T) as ROW PAIRS (W[2 i2][j], W[2 i2 + 1][j]),
 // so that y_{2 i2}, y_{2 i2 + 1} accumulate together in one FFMA2 with dx_j broadcast.
+//   row-major  : entry (i2, j), j <= 2 i2 + 1, at i2 (i2 + 1) + j
+//   column-major (OPT_JMAJOR): entry (j, i2), i2 >= j/2, at wj_off(j) + i2 - j/2; every column padded to an even count
 template <int LD>
-struct MvnParams {
-    static constexpr int NWP = (LD / 2) * (LD / 2 + 1);
-    float2 Wp[NWP];
-    float2 mu2[LD / 2];
+struct alignas(16) MvnParams {
+    static constexpr int H = LD / 2;
+    __host__ __device__ static constexpr int wj_cnt(int j) { return ((H - j / 2) + 1) & ~1; }
+    __host__ __device__ static constexpr int wj_off(int j) { int o = 0; for (int t = 0; t < j; ++t) o += wj_cnt(t); return o; }
+    static constexpr int NW_ROW = H * (H + 1);
+    static constexpr int NW_COL = wj_off(LD);
+    static constexpr int NW = NW_ROW > NW_COL ? NW_ROW : NW_COL;
+    float2 W[NW];
+    float2 mu2[H];
     float c0;
 };
 
@@ -122,13 +137,6 @@ struct StageLayout {
     static constexpr int LDS = (C % 2 == 1) ? LD : LD + 4;        // staged row stride (floats): odd #chunks
     static constexpr int ROWS = 64 * LDS;                         // 32 x r1 rows, 32 x r2 rows
     static constexpr int FLOATS = ROWS + 96;                      // + idx[64] + accept word[32]
-};
-
-// constants broadcast from shared memory: Wp | mu2 | eps2 | shift2   (float2 units)
-template <int LD>
-struct ConstLayout {
-    static constexpr int NWP = MvnParams<LD>::NWP;
-    static constexpr int MU = NWP, EPS = NWP + LD / 2, SHIFT = NWP + LD, TOTAL = NWP + 3 * LD / 2;
 };
 
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src)
@@ -148,47 +156,81 @@ __device__ __forceinline__ T warp_sum(T v)
     return v;
 }
 
-// log-density of the closed-form family: c0 - 0.5 |W (x - mu)|^2, constants from shared memory
-// (LDS.128 broadcasts), two rows of W per FFMA2.
-template <int LD>
-__device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ sc, float c0, const float2 (&x2)[LD / 2])
+// predicated 16-byte async copy (no branch: the predicate rides on the LDGSTS)
+__device__ __forceinline__ void cp_async16_if(bool p, float* smem_dst, const float* gmem_src)
 {
-    using CL = ConstLayout<LD>;
+    const uint32_t s = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.b32 q, %2, 0;\n\t@q cp.async.cg.shared.global [%0], [%1], 16;\n\t}\n"
+                 ::"r"(s), "l"(gmem_src), "r"((int)p) : "memory");
+}
+
+// log-density of the closed-form family: c0 - 0.5 |W (x - mu)|^2.  `Wc` / `muc` point either at the kernel
+// parameters (constant bank: ptxas stages them through uniform registers, LDCU.128, and feeds FFMA2 its
+// .F32x2 operand from there) or at a shared-memory copy (LDS.128 broadcasts).
+template <int LD, bool JMAJOR>
+__device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ Wc, const float2* __restrict__ muc, float c0,
+                                                const float2 (&x2)[LD / 2])
+{
+    using MP = MvnParams<LD>;
+    constexpr int H = LD / 2;
     float dx[LD];
 #pragma unroll
-    for (int k2 = 0; k2 < LD / 2; k2 += 2) {
-        const float4 m = *reinterpret_cast<const float4*>(sc + CL::MU + k2);
+    for (int k2 = 0; k2 < H; k2 += 2) {
+        const float4 m = *reinterpret_cast<const float4*>(muc + k2);
         const float2 a = fsub2(x2[k2], make_float2(m.x, m.y));
         const float2 b = fsub2(x2[k2 + 1], make_float2(m.z, m.w));
         dx[2 * k2] = a.x; dx[2 * k2 + 1] = a.y; dx[2 * k2 + 2] = b.x; dx[2 * k2 + 3] = b.y;
     }
     float2 q2 = make_float2(0.f, 0.f);
+    if constexpr (JMAJOR) {
+        float2 y[H];
 #pragma unroll
-    for (int i2 = 0; i2 < LD / 2; ++i2) {
-        float2 y = make_float2(0.f, 0.f);
+        for (int i2 = 0; i2 < H; ++i2) y[i2] = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int j = 0; j < 2 * i2 + 2; j += 2) {
-            const float4 w = *reinterpret_cast<const float4*>(sc + i2 * (i2 + 1) + j);
-            y = ffma2(make_float2(w.x, w.y), make_float2(dx[j], dx[j]), y);
-            y = ffma2(make_float2(w.z, w.w), make_float2(dx[j + 1], dx[j + 1]), y);
+        for (int j = 0; j < LD; ++j) {
+            const float2 dj = make_float2(dx[j], dx[j]);
+#pragma unroll
+            for (int t = 0; t < MP::wj_cnt(j); t += 2) {
+                const float4 w = *reinterpret_cast<const float4*>(Wc + MP::wj_off(j) + t);
+                const int i2 = j / 2 + t;
+                y[i2] = ffma2(make_float2(w.x, w.y), dj, y[i2]);
+                if (i2 + 1 < H) y[i2 + 1] = ffma2(make_float2(w.z, w.w), dj, y[i2 + 1]);
+            }
         }
-        q2 = ffma2(y, y, q2);
+#pragma unroll
+        for (int i2 = 0; i2 < H; ++i2) q2 = ffma2(y[i2], y[i2], q2);
+    } else {
+#pragma unroll
+        for (int i2 = 0; i2 < H; ++i2) {
+            float2 y = make_float2(0.f, 0.f);
+#pragma unroll
+            for (int j = 0; j < 2 * i2 + 2; j += 2) {
+                const float4 w = *reinterpret_cast<const float4*>(Wc + i2 * (i2 + 1) + j);
+                y = ffma2(make_float2(w.x, w.y), make_float2(dx[j], dx[j]), y);
+                y = ffma2(make_float2(w.z, w.w), make_float2(dx[j + 1], dx[j + 1]), y);
+            }
+            q2 = ffma2(y, y, q2);
+        }
     }
     return fmaf(-0.5f, q2.x + q2.y, c0);
 }
 
 // FULL: a single block covering every column (the common case) — no per-column masks.
-template <int LD, bool ACC, bool FULL, int WARPS, int MINB>
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
     using SL = StageLayout<LD>;
-    using CL = ConstLayout<LD>;
+    using MP = MvnParams<LD>;
     constexpr int C = SL::C, LDS = SL::LDS, ZS = zslot(LD), CP = ZS / 4, RPI = 32 / CP, STAGES = 2, H = LD / 2;
+    constexpr bool W_SMEM = OPT & OPT_W_SMEM, JMAJOR = OPT & OPT_JMAJOR, IDX_VEC = OPT & OPT_IDX_VEC,
+                   S2_SMEM = (OPT & OPT_S2_SMEM) && ACC;
+    constexpr int NWC = JMAJOR ? MP::NW_COL : MP::NW_ROW;
     extern __shared__ __align__(16) float smem[];
-    __shared__ __align__(16) float2 sc[CL::TOTAL];
     __shared__ unsigned int red_cnt[2];
     __shared__ float red_s2[ACC ? LD : 1];
+    __shared__ __align__(16) float2 scW[W_SMEM ? NWC + H : 1];
+    __shared__ float2 s2s[S2_SMEM ? H * WARPS * 32 : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* wbase = smem + warp * (STAGES * SL::FLOATS);
@@ -199,12 +241,11 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
 
     if (threadIdx.x < 2) red_cnt[threadIdx.x] = 0u;
     if (ACC && threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
-    for (int t = threadIdx.x; t < CL::NWP + H; t += WARPS * 32) sc[t] = t < CL::NWP ? P.Wp[t] : P.mu2[t - CL::NWP];
-    if (threadIdx.x < H) {
-        sc[CL::EPS + threadIdx.x] = make_float2(a.eps[2 * threadIdx.x], a.eps[2 * threadIdx.x + 1]);
-        sc[CL::SHIFT + threadIdx.x] = make_float2(a.shift[2 * threadIdx.x], a.shift[2 * threadIdx.x + 1]);
-    }
+    if (W_SMEM)
+        for (int t = threadIdx.x; t < NWC + H; t += WARPS * 32) scW[t] = t < NWC ? P.W[t] : P.mu2[t - NWC];
     __syncthreads();
+    const float2* Wc = W_SMEM ? scW : P.W;
+    const float2* muc = W_SMEM ? scW + NWC : P.mu2;
 
     float2 x2[H];
 #pragma unroll
@@ -214,13 +255,14 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     }
     float lp = a.logp[cl];
 
-    float2 s1[ACC ? H : 1], s2[ACC ? H : 1];
+    float2 s1[ACC ? H : 1], s2[(ACC && !S2_SMEM) ? H : 1];
     if (ACC) {
 #pragma unroll
         for (int k = 0; k < H; ++k) {
             s1[k].x = (2 * k < a.d) ? a.S1[(size_t)(2 * k) * a.ldx + cl] : 0.f;
             s1[k].y = (2 * k + 1 < a.d) ? a.S1[(size_t)(2 * k + 1) * a.ldx + cl] : 0.f;
-            s2[k] = make_float2(0.f, 0.f);
+            if (S2_SMEM) s2s[k * (WARPS * 32) + threadIdx.x] = make_float2(0.f, 0.f);
+            else s2[k] = make_float2(0.f, 0.f);
         }
     }
 
@@ -229,11 +271,13 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     int cnt_run = 0, cnt_win = 0, cnt_acc = 0;
 
     // ---- producer side of the per-warp pipeline -------------------------------------------
-    // lane -> (row within a group of RPI rows, 16-byte piece of the row slot): lane-only, so the
-    // copy loop below has compile-time shared-memory offsets
+    // lane -> (staged row, 16-byte piece of the row slot), lane-only so that the copy loop has compile-time
+    // shared-memory offsets.  IDX_VEC: a lane group owns RPL consecutive staged rows (their indices are read
+    // with LDS.128); otherwise copy instruction `it` covers rows it*RPI .. it*RPI+RPI-1.
+    constexpr int RPL = 64 / RPI;                       // copy instructions per stage
     const int lrow = lane / CP, lpiece = lane % CP;
     const bool pact = lpiece < C;
-    const int soff = lrow * LDS + lpiece * 4;
+    const int soff = (IDX_VEC ? lrow * RPL : lrow) * LDS + lpiece * 4;
     int pg = 0, pb = 0;
     auto prefetch = [&](int stage) {
         float* st = wbase + stage * SL::FLOATS;
@@ -249,10 +293,21 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         idx[64 + lane] = w.z;
         __syncwarp();
         const float* zb = a.Z + lpiece * 4;
+        if constexpr (IDX_VEC) {
+            uint32_t rows[RPL];
 #pragma unroll
-        for (int it = 0; it < 64 / RPI; ++it) {
-            const uint32_t row = idx[it * RPI + lrow];
-            if (pact) cp_async16(st + it * RPI * LDS + soff, zb + (size_t)row * ZS);
+            for (int v = 0; v < RPL / 4; ++v) {
+                const uint4 t = *reinterpret_cast<const uint4*>(idx + lrow * RPL + 4 * v);
+                rows[4 * v] = t.x; rows[4 * v + 1] = t.y; rows[4 * v + 2] = t.z; rows[4 * v + 3] = t.w;
+            }
+#pragma unroll
+            for (int it = 0; it < RPL; ++it) cp_async16_if(pact, st + it * LDS + soff, zb + (size_t)rows[it] * ZS);
+        } else {
+#pragma unroll
+            for (int it = 0; it < RPL; ++it) {
+                const uint32_t row = idx[it * RPI + lrow];
+                cp_async16_if(pact, st + it * RPI * LDS + soff, zb + (size_t)row * ZS);
+            }
         }
         if (!FULL) { if (++pb == nb) { pb = 0; ++pg; } } else { ++pg; }
     };
@@ -293,16 +348,15 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         const uint32_t wacc = idx[64 + lane];
 #pragma unroll
         for (int q8 = 0; q8 < (LD + 7) / 8; ++q8) {
-            if (FULL || ((mask >> (8 * q8)) & 0xFFu)) {      // warp-uniform
+            if ((OPT & OPT_ABL_NOJIT) ? false : (FULL || ((mask >> (8 * q8)) & 0xFFu))) {      // warp-uniform
                 const u32x4 wn = philox4x32_10(cid, g_lo, ((uint32_t)cb << 16) | (uint32_t)(1 + q8), g_hi, a.keys);
                 const uint32_t ww[4] = {wn.x, wn.y, wn.z, wn.w};
 #pragma unroll
                 for (int j = 0; j < 4; j += 2) {
                     const int k2 = 4 * q8 + j;               // column pair index
                     if (k2 < H) {
-                        const float4 e = *reinterpret_cast<const float4*>(sc + CL::EPS + k2);
-                        xp[k2] = ffma2(cs2, xp[k2], ffma2(make_float2(e.x, e.y), box_muller16(ww[j]), x2[k2]));
-                        xp[k2 + 1] = ffma2(cs2, xp[k2 + 1], ffma2(make_float2(e.z, e.w), box_muller16(ww[j + 1]), x2[k2 + 1]));
+                        xp[k2] = ffma2(cs2, xp[k2], ffma2(a.eps2[k2], box_muller16(ww[j]), x2[k2]));
+                        xp[k2 + 1] = ffma2(cs2, xp[k2 + 1], ffma2(a.eps2[k2 + 1], box_muller16(ww[j + 1]), x2[k2 + 1]));
                     }
                 }
             }
@@ -315,7 +369,7 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             }
         }
 
-        const float lpp = mvn_logdensity<LD>(sc, P.c0, xp);
+        const float lpp = (OPT & OPT_ABL_NOQUAD) ? xp[0].x + xp[H - 1].y : mvn_logdensity<LD, JMAJOR>(Wc, muc, P.c0, xp);
         const float u = uniform01(wacc);
         const float logu = __logf(u);
         const float delta = lpp - lp;
@@ -353,12 +407,11 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             }
             if (ACC) {
 #pragma unroll
-                for (int k = 0; k < H; k += 2) {
-                    const float4 sh = *reinterpret_cast<const float4*>(sc + CL::SHIFT + k);
-                    const float2 t0 = fsub2(x2[k], make_float2(sh.x, sh.y));
-                    const float2 t1 = fsub2(x2[k + 1], make_float2(sh.z, sh.w));
-                    s1[k] = fadd2(s1[k], t0);         s1[k + 1] = fadd2(s1[k + 1], t1);
-                    s2[k] = ffma2(t0, t0, s2[k]);     s2[k + 1] = ffma2(t1, t1, s2[k + 1]);
+                for (int k = 0; k < H; ++k) {
+                    const float2 t = fsub2(x2[k], a.shift2[k]);
+                    s1[k] = fadd2(s1[k], t);
+                    if (S2_SMEM) { float2& r = s2s[k * (WARPS * 32) + threadIdx.x]; r = ffma2(t, t, r); }
+                    else s2[k] = ffma2(t, t, s2[k]);
                 }
             }
             lp_gen0 = lp;
@@ -393,7 +446,8 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         if (ACC) {
 #pragma unroll
             for (int k = 0; k < LD; ++k) {
-                const float v = warp_sum(active ? ((k & 1) ? s2[k / 2].y : s2[k / 2].x) : 0.f);
+                const float2 sv = S2_SMEM ? s2s[(k / 2) * (WARPS * 32) + threadIdx.x] : s2[S2_SMEM ? 0 : k / 2];
+                const float v = warp_sum(active ? ((k & 1) ? sv.y : sv.x) : 0.f);
                 if (lane == 0) atomicAdd(&red_s2[k], v);
             }
         }
@@ -411,10 +465,6 @@ template <int LD>
 __global__ void mvn_eval_kernel(const float* __restrict__ X, int n, int ldx, int d, float* __restrict__ out,
                                 const __grid_constant__ MvnParams<LD> P)
 {
-    using CL = ConstLayout<LD>;
-    __shared__ __align__(16) float2 sc[CL::TOTAL];
-    for (int t = threadIdx.x; t < CL::NWP + LD / 2; t += blockDim.x) sc[t] = t < CL::NWP ? P.Wp[t] : P.mu2[t - CL::NWP];
-    __syncthreads();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float2 x2[LD / 2];
@@ -423,7 +473,7 @@ __global__ void mvn_eval_kernel(const float* __restrict__ X, int n, int ldx, int
         x2[k].x = (2 * k < d) ? X[(size_t)(2 * k) * ldx + i] : 0.f;
         x2[k].y = (2 * k + 1 < d) ? X[(size_t)(2 * k + 1) * ldx + i] : 0.f;
     }
-    out[i] = mvn_logdensity<LD>(sc, P.c0, x2);
+    out[i] = mvn_logdensity<LD, false>(P.W, P.mu2, P.c0, x2);
 }
 
 }  // namespace demcz
