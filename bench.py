@@ -59,12 +59,33 @@ def workload(name, chains_per_gpu, archive_rows):
         return dict(name="C1 example_normpdf d=5 MvNormal N=100", d=d, mu=mu, Sigma=S, kind="mvn", K=10,
                     blocks=[list(range(d))], anneal=False, autostop=False, gamma=2.38,
                     chains_per_gpu=chains_per_gpu or 100, archive_rows=archive_rows or 150)
+    if name in ("c2", "c5"):   # test/example_linreg.jl scaled up: the tensor-core GEMM likelihood
+        n, p, N = (1_000_000, 32, 4096) if name == "c2" else (10_000_000, 64, 32768)
+        return dict(name=f"{name.upper()} linreg n={n} x p={p} (example_linreg.jl generator), K=10, gamma=2.0", d=p, kind="linreg",
+                    n=n, K=10, blocks=[list(range(p))], anneal=False, autostop=False, gamma=2.0,
+                    chains_per_gpu=chains_per_gpu or N, archive_rows=archive_rows or 2 * (chains_per_gpu or N) * 8)
     raise SystemExit(f"unknown workload {name}")
+
+
+def linreg_data(n, p, seed=319531501):
+    """test/example_linreg.jl:9-29: intercept + (p-1) unit-variance regressors with pairwise correlation 0.25,
+    beta = 1 + 3 U(0,1), y = X beta + N(0,1)."""
+    rng = np.random.default_rng(seed)
+    X = np.empty((n, p), order="F")
+    X[:, 0] = 1.0
+    z0 = rng.standard_normal(n, dtype=np.float32).astype(np.float64)
+    for k in range(1, p):
+        X[:, k] = 0.5 * z0 + np.sqrt(0.75) * rng.standard_normal(n, dtype=np.float32)
+    beta = 1 + 3 * rng.random(p)
+    y = X @ beta + rng.standard_normal(n)
+    return X, y
 
 
 def make_archive(w, rows, seed=7):
     """Z0 ~ N(mu, 4*Sigma): over-dispersed start, identical on every rank (replicated archive)."""
     rng = np.random.default_rng(seed)
+    if w["kind"] == "linreg":      # around the OLS point, 3x the posterior scale
+        return w["bols"] + 3.0 * w["post_sd"] * rng.standard_normal((rows, w["d"]))
     L = np.linalg.cholesky(w["Sigma"])
     Z = np.empty((rows, w["d"]), order="F")
     step = 1 << 20
@@ -138,7 +159,10 @@ class ClockSampler:
 def cpu_run(w, *, chains, gens, archive_rows, threads, faithful=False, seed=31953150):
     from oracle import demcz_oracle as orc      # the checker, timed as the CPU baseline (never on the product path)
     co = orc.COracle(build=not os.path.exists(os.path.join(ROOT, "oracle", "libdemcz_oracle.so")))
-    lik = orc.MvNormalLik(w["mu"], w["Sigma"], drop_constant=(w["kind"] == "quad"))
+    if w["kind"] == "linreg":
+        lik = orc.LinRegLik(w["X"], w["y"])
+    else:
+        lik = orc.MvNormalLik(w["mu"], w["Sigma"], drop_constant=(w["kind"] == "quad"))
     Z0 = make_archive(w, max(archive_rows, chains), seed=7)
     kw = dict(anneal=w["anneal"], store_chain=False, nthreads=threads, z_rowmajor=0 if faithful else 1,
               index_mode=1 if faithful else 0)
@@ -149,23 +173,55 @@ def cpu_run(w, *, chains, gens, archive_rows, threads, faithful=False, seed=3195
     return chains * gens / dt, dt
 
 
+def cpu_sample_size(w, threads):
+    if w["kind"] == "linreg":      # one proposal streams the whole data set: a few chains per thread is already seconds
+        return threads * 2, 2
+    chains = min(w["chains_per_gpu"], 16384)
+    return max(chains // threads * threads, min(w["chains_per_gpu"], threads)), 20
+
+
 def cpu_baseline(w, budget_s=12.0):
     threads = os.cpu_count() or 1
     arch = min(w["archive_rows"], 1 << 20)
-    chains = min(w["chains_per_gpu"], 16384)
-    chains = max(chains // threads * threads, min(w["chains_per_gpu"], threads))
-    v, dt = cpu_run(w, chains=chains, gens=20, archive_rows=arch, threads=threads)            # calibrate
-    gens = int(max(20, min(5000, budget_s * v / chains)))
+    chains, g0 = cpu_sample_size(w, threads)
+    v, dt = cpu_run(w, chains=chains, gens=g0, archive_rows=arch, threads=threads)            # calibrate
+    gens = int(max(g0, min(5000, budget_s * v / chains)))
     v, dt = cpu_run(w, chains=chains, gens=gens, archive_rows=arch, threads=threads)
     out = dict(value=v, unit="chain-updates/s", cores=threads, kind="port",
                sample=f"{chains} chains x {gens} generations, archive {max(arch, chains)} rows, FP64, O(1) index draw, "
                       f"row-major archive, OpenMP over chains ({dt:.1f} s)")
     # reference-faithful serial mode: O(M) index-set construction per proposal (src/demcz.jl:176-178), 1 thread
-    fch = min(chains, 64)
-    fv, fdt = cpu_run(w, chains=fch, gens=10, archive_rows=min(arch, 1 << 17), threads=1, faithful=True)
-    out["faithful_serial"] = dict(value=fv, cores=1, sample=f"{fch} chains x 10 generations, archive {max(min(arch, 1 << 17), fch)} rows "
+    fch = min(chains, 64) if w["kind"] != "linreg" else 4
+    fg = 10 if w["kind"] != "linreg" else 2
+    fv, fdt = cpu_run(w, chains=fch, gens=fg, archive_rows=min(arch, 1 << 17), threads=1, faithful=True)
+    out["faithful_serial"] = dict(value=fv, cores=1, sample=f"{fch} chains x {fg} generations, archive {max(min(arch, 1 << 17), fch)} rows "
                                                             f"({fdt:.1f} s), collect(1:M)+deleteat! per proposal")
     return out
+
+
+def prepare_data(w):
+    """Synthetic likelihood data of the workload's shape (identical on every rank)."""
+    if w["kind"] == "linreg" and "X" not in w:
+        w["X"], w["y"] = linreg_data(w["n"], w["d"])
+        XtX = w["X"].T @ w["X"]
+        w["bols"] = np.linalg.solve(XtX, w["X"].T @ w["y"])
+        w["post_sd"] = np.sqrt(np.diag(np.linalg.inv(XtX)))
+
+
+def measure_tf32_peak():
+    """Dense TF32 tensor throughput of this GPU (cuBLAS via torch.matmul, 8192^3, best of 10): the denominator of
+    the linreg roofline.  Library call used for the PEAK only."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(8192, 8192, device="cuda"); b = torch.randn(8192, 8192, device="cuda")
+    for _ in range(3):
+        a @ b
+    best = 1e9
+    for _ in range(10):
+        e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+        e0.record(); a @ b; e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1))
+    return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
 
 
 # ------------------------------------------------------------------------------------------------
@@ -176,7 +232,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c4")
-    ap.add_argument("--gens-per-step", type=int, default=100)
+    ap.add_argument("--gens-per-step", type=int, default=0)
     ap.add_argument("--chains-per-gpu", type=int, default=0)
     ap.add_argument("--archive-rows", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -189,10 +245,13 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
     w = workload(args.workload, args.chains_per_gpu, args.archive_rows)
-    d, K, gps = w["d"], w["K"], args.gens_per_step
+    d, K = w["d"], w["K"]
+    gps = args.gens_per_step or (10 if w["kind"] == "linreg" else 100)
     cfg = dict(workload=w["name"], chains_per_gpu=w["chains_per_gpu"], chains_total=w["chains_per_gpu"] * max(world, 1),
                generations_per_step=gps, K=K, Nblocks=len(w["blocks"]), archive_rows_initial=w["archive_rows"],
-               archive="replicated, ring buffer", l2="archive > L2 (126 MB): random gathers miss L2; no flush needed",
+               archive="replicated, ring buffer",
+               l2=("X_hi + X_lo (2 x 4 n p bytes) > L2 (126 MB) and re-streamed every generation; no flush needed" if w["kind"] == "linreg"
+                   else "archive > L2 (126 MB): random gathers miss L2; no flush needed"),
                parallelism=f"chains sharded x{world}, NCCL all-gather of appended rows every K generations")
 
     # ---------------------------------------------------------------- reference arm (CPU) -------
@@ -200,11 +259,11 @@ def main():
         if rank != 0:
             return 0
         threads = os.cpu_count() or 1
-        chains = min(w["chains_per_gpu"], 16384)
-        chains = max(chains // threads * threads, min(w["chains_per_gpu"], threads))
+        prepare_data(w)
+        chains, g0 = cpu_sample_size(w, threads)
         arch = min(w["archive_rows"], 1 << 20)
-        v, _ = cpu_run(w, chains=chains, gens=10, archive_rows=arch, threads=threads)
-        gens = int(max(10, min(2000, 4.0 * v / chains)))                     # ~4 s per step
+        v, _ = cpu_run(w, chains=chains, gens=g0, archive_rows=arch, threads=threads)
+        gens = int(max(g0, min(2000, 4.0 * v / chains)))                     # ~4 s per step
         for _ in range(min(args.warmup, 1)):
             cpu_run(w, chains=chains, gens=gens, archive_rows=arch, threads=threads)
         t = 0.0
@@ -261,7 +320,12 @@ def main():
     cap = max(M0 + N_global * 16, 64 << 20) if args.workload != "c1" else 0
     if cap:
         cap = (cap + N_global - 1) // N_global * N_global            # append segments never straddle the ring end
-    logobj = (DEMC.QuadraticLogobj(w["mu"]) if w["kind"] == "quad" else DEMC.MvNormalLogpdf(w["mu"], w["Sigma"]))
+    prepare_data(w)
+    if w["kind"] == "linreg":
+        logobj = DEMC.LinRegLoglik(w["X"], w["y"])
+        cap = 0
+    else:
+        logobj = (DEMC.QuadraticLogobj(w["mu"]) if w["kind"] == "quad" else DEMC.MvNormalLogpdf(w["mu"], w["Sigma"]))
     Z0 = make_archive(w, M0)
     s = ddist.make_sharded_sampler(logobj, d, N_global=N_global, rank=rank, world=world, device=local_rank, K=K,
                                    Ngeneration=G_total, blockindex=w["blocks"], eps_scale=1e-5 * np.ones(d), γ=w["gamma"],
@@ -324,7 +388,25 @@ def main():
     pinfo = s.run(gps)
     s.set_profile(False)
     roof = None
-    if pinfo["step_launches"] > 0:
+    if pinfo["step_launches"] > 0 and w["kind"] == "linreg":
+        n_l = pinfo["step_launches"]
+        avg_ms = pinfo["step_kernel_ms"] / n_l
+        flops = 2.0 * w["n"] * d * N_local                       # FP32-equivalent flops of X (n x p) . B^T (p x N)
+        achieved = flops / (avg_ms * 1e-3) / 1e12
+        tf32 = measure_tf32_peak()
+        bf16 = None
+        try:
+            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+        except Exception:
+            pass
+        roof = dict(bound="tensor", kernel="linreg_ssr_kernel (tcgen05 kind::tf32, 3xTF32)", achieved=achieved, peak=tf32 / 3.0,
+                    unit="TFLOP/s", frac=achieved / (tf32 / 3.0), traffic=None,
+                    peak_source=f"TF32 dense measured live with torch.matmul 8192^3 = {tf32:.0f} TFLOP/s, / 3 for the 3xTF32 split "
+                                f"(MEASURED_PEAKS.json bf16_tflops = {bf16})",
+                    tensor_issued_tflops=3 * achieved, tensor_frac_of_tf32_peak=3 * achieved / tf32, launch_us=avg_ms * 1e3,
+                    flops_per_launch=flops, kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
+        acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
+    elif pinfo["step_launches"] > 0:
         n_l = pinfo["step_launches"]
         avg_ms = pinfo["step_kernel_ms"] / n_l
         G_f = gps / n_l
@@ -357,8 +439,8 @@ def main():
     if rank == 0:
         print(json.dumps(dict(metric="chain-updates/s", value=value, unit="chain-updates/s", n_gpus=world, steps=args.steps,
                               warmup=args.warmup, ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps,
-                              higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
-                              clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                              higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (linreg: 3xTF32 products, FP32 accumulate, FP64 sums)" if w["kind"] == "linreg" else "f32",
+                              data="synthetic", config=cfg, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                               accepted_fraction=acc_frac, proposals_per_s=value * len(w["blocks"]))))
     return 0
 

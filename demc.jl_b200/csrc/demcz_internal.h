@@ -22,7 +22,7 @@ struct demcz_ctx {
     int ldx = 0;         // SoA leading dimension (N rounded up to 32)
     int ZS = 0;          // archive row slot in floats (power of two >= LD for the closed-form path)
     demcz::PhiloxKeys keys{};
-    float shift[32] = {0};
+    float shift[64] = {0};
 
     int lik_kind = DEMCZ_LIK_NONE;
     std::vector<float> mvn_mu, mvn_W;   // W = L^-1, row-major d x d (lower)
@@ -36,6 +36,7 @@ struct demcz_ctx {
     int64_t zcap = 0;
     int64_t M = 0;              // rows appended so far (valid rows = min(M, zcap))
     float* dT = nullptr;        // temperature table
+    std::vector<float> hT;      // its host copy (the linreg path passes T by value)
     float* dhist = nullptr;     // [G][d][N]
     float* dlphist = nullptr;   // [G][N]
     uint32_t* tr_r1 = nullptr; uint32_t* tr_r2 = nullptr; float* tr_u = nullptr; float* tr_xprop = nullptr;
@@ -77,6 +78,11 @@ int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);
 void demcz_comm_destroy_internal(demcz_ctx* c);
 
 // demcz_linreg.cu
-int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, float* out);
-int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append);
+// out_dev == nullptr: evaluate the context's own N chains into its FP64 log-objective array
+int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_dev);
+int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half);
 void demcz_linreg_free(demcz_ctx* c);
+double* demcz_linreg_lp(demcz_ctx* c);           // [ldx] FP64 log-objective of the chains (logpi ~ -n/2 needs more than FP32)
+double* demcz_linreg_lphist(demcz_ctx* c);       // [G][N]
+unsigned long long demcz_linreg_launches(demcz_ctx* c);
+double demcz_linreg_profile_ms(demcz_ctx* c, long long* launches);

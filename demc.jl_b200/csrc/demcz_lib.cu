@@ -494,7 +494,7 @@ static int eval_state_logp(demcz_ctx* c)
     if (c->lik_kind == DEMCZ_LIK_MVN) {
         CU(c, launch_eval(c, c->dX, c->o.N, c->ldx, c->dlogp));
     } else if (c->lik_kind == DEMCZ_LIK_LINREG) {
-        int rc = demcz_linreg_eval(c, c->dX, c->o.N, c->ldx, c->dlogp);
+        int rc = demcz_linreg_eval(c, c->dX, c->o.N, c->ldx, nullptr);
         if (rc != DEMCZ_OK) return rc;
     } else {
         return demcz_fail(c, DEMCZ_ERR_INVALID, "no likelihood set");
@@ -514,8 +514,12 @@ extern "C" int demcz_set_state(demcz_ctx* c, const double* X, const double* logp
     CU(c, cudaGetLastError());
     if (logp) {
         CU(c, cudaMemcpyAsync(stage + (size_t)N * d, logp, (size_t)N * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-        f64_to_f32_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage + (size_t)N * d, N, c->dlogp);
-        CU(c, cudaGetLastError());
+        if (c->lik_kind == DEMCZ_LIK_LINREG) {
+            CU(c, cudaMemcpyAsync(demcz_linreg_lp(c), stage + (size_t)N * d, (size_t)N * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+        } else {
+            f64_to_f32_kernel<<<grid1d(N), 256, 0, c->stream>>>(stage + (size_t)N * d, N, c->dlogp);
+            CU(c, cudaGetLastError());
+        }
     }
     CU(c, cudaStreamSynchronize(c->stream));      // the caller's buffers are borrowed for the call only
     c->state_set = true;
@@ -532,6 +536,7 @@ extern "C" int demcz_set_temperature_table(demcz_ctx* c, const double* T, int64_
     if (c->dT) { cudaFree(c->dT); c->dT = nullptr; }
     CU(c, cudaMalloc((void**)&c->dT, (size_t)(len ? len : 1) * sizeof(float)));
     CU(c, cudaMemcpy(c->dT, Tf.data(), (size_t)len * sizeof(float), cudaMemcpyHostToDevice));
+    c->hT = Tf;
     return DEMCZ_OK;
 }
 
@@ -583,7 +588,7 @@ static int start_rhat_window(demcz_ctx* c)
     double sums[64];
     CU(c, cudaMemcpyAsync(sums, c->d_scratch, (size_t)o.d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    for (int k = 0; k < 32; ++k) c->shift[k] = k < o.d ? (float)(sums[k] / o.N) : 0.f;
+    for (int k = 0; k < 64; ++k) c->shift[k] = k < o.d ? (float)(sums[k] / o.N) : 0.f;
     CU(c, cudaMemcpyAsync(c->dshift, c->shift, (size_t)o.d * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     return DEMCZ_OK;
 }
@@ -639,6 +644,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     if (max_generations > 0 && g_begin + max_generations < g_end) g_end = g_begin + max_generations;
     const int every = o.autostop_every, nhalf = every / 2;
     size_t n_launch = 0;
+    const unsigned long long lin_launch0 = demcz_linreg_launches(c);
+    if (c->lik_kind == DEMCZ_LIK_LINREG) demcz_linreg_profile_ms(c, nullptr);      // drop brackets of earlier calls
     bool stopped = false;
 
     int64_t g = g_begin;
@@ -660,7 +667,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         const bool append = (gb % o.K) == 0;
 
         if (c->lik_kind == DEMCZ_LIK_LINREG) {
-            rc = demcz_linreg_generations(c, g, n_gens, append);
+            rc = demcz_linreg_generations(c, g, n_gens, append, acc, half);
             if (rc != DEMCZ_OK) return rc;
         } else {
             // ---- launch ------------------------------------------------------------------------
@@ -754,7 +761,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         unsigned long long acc_total = 0;
         CU(c, cudaMemcpy(&acc_total, c->d_counters + 1, sizeof acc_total, cudaMemcpyDeviceToHost));
         info->accepted = (int64_t)acc_total;
-        info->step_launches = (int64_t)n_launch;
+        info->step_launches = (int64_t)n_launch + (int64_t)(demcz_linreg_launches(c) - lin_launch0);
         float ms = 0.f;
         CU(c, cudaEventElapsedTime(&ms, c->ev_run[0], c->ev_run[1]));
         info->device_ms = ms;
@@ -765,6 +772,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
                 CU(c, cudaEventElapsedTime(&t, c->ev_pool[2 * i], c->ev_pool[2 * i + 1]));
                 tot += t;
             }
+            if (c->lik_kind == DEMCZ_LIK_LINREG) tot = demcz_linreg_profile_ms(c, nullptr);
             info->step_kernel_ms = tot;
         }
     }
@@ -802,7 +810,10 @@ extern "C" int demcz_get_chain(demcz_ctx* c, double* chain, double* log_obj)
     if (G == 0) return DEMCZ_OK;
     // device history is [g][k][chain] in FP32 == Julia's column-major N x d x G
     if (chain) { int rc = d2h_as_f64(c, c->dhist, G * d * N, chain); if (rc) return rc; }
-    if (log_obj) { int rc = d2h_as_f64(c, c->dlphist, G * N, log_obj); if (rc) return rc; }
+    if (log_obj && c->lik_kind == DEMCZ_LIK_LINREG) {
+        CU(c, cudaMemcpyAsync(log_obj, demcz_linreg_lphist(c), G * N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+    } else if (log_obj) { int rc = d2h_as_f64(c, c->dlphist, G * N, log_obj); if (rc) return rc; }
     return DEMCZ_OK;
 }
 
@@ -818,7 +829,9 @@ extern "C" int demcz_get_state(demcz_ctx* c, double* X, double* logp)
         CU(c, cudaGetLastError());
         CU(c, cudaMemcpyAsync(X, stage, (size_t)N * d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
     }
-    if (logp) {
+    if (logp && c->lik_kind == DEMCZ_LIK_LINREG) {
+        CU(c, cudaMemcpyAsync(logp, demcz_linreg_lp(c), (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    } else if (logp) {
         f32_to_f64_kernel<<<grid1d(N), 256, 0, c->stream>>>(c->dlogp, N, stage + (size_t)N * d);
         CU(c, cudaGetLastError());
         CU(c, cudaMemcpyAsync(logp, stage + (size_t)N * d, (size_t)N * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
@@ -905,11 +918,14 @@ extern "C" int demcz_eval_logdensity(demcz_ctx* c, const double* X, int64_t n, d
     if (e == cudaSuccess) {
         import_soa_kernel<<<grid1d(n), 256, 0, c->stream>>>(stage, n, d, ld, xf);
         float* of = xf + (size_t)ld * d;
-        if (c->lik_kind == DEMCZ_LIK_MVN) e = launch_eval(c, xf, (int)n, (int)ld, of);
-        else rc = demcz_linreg_eval(c, xf, (int)n, (int)ld, of);
-        if (e == cudaSuccess && rc == DEMCZ_OK) {
-            f32_to_f64_kernel<<<grid1d(n), 256, 0, c->stream>>>(of, n, stage + (size_t)n * d);
-            e = cudaGetLastError();
+        if (c->lik_kind == DEMCZ_LIK_MVN) {
+            e = launch_eval(c, xf, (int)n, (int)ld, of);
+            if (e == cudaSuccess) {
+                f32_to_f64_kernel<<<grid1d(n), 256, 0, c->stream>>>(of, n, stage + (size_t)n * d);
+                e = cudaGetLastError();
+            }
+        } else {
+            rc = demcz_linreg_eval(c, xf, (int)n, (int)ld, stage + (size_t)n * d);
         }
     }
     if (e == cudaSuccess && rc == DEMCZ_OK) e = cudaMemcpyAsync(out, stage + (size_t)n * d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, c->stream);

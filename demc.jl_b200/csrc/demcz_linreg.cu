@@ -1,12 +1,832 @@
-// demcz_linreg.cu — linear-regression Gaussian log-likelihood (test/example_linreg.jl:32) path.
-// Placeholder translation unit: the tcgen05 implementation lands in a later commit.
+// demcz_linreg.cu — the linear-regression Gaussian log-likelihood path of the DEMCz generation loop:
+//     logobj(b) = -0.5 * sum((y .- X*b).^2)                       (reference test/example_linreg.jl:32)
+// evaluated for ALL chains of a generation at once as the one dense contraction of the sampler,
+// X (n x p) times the proposals (N x p)^T, on the 5th-generation tensor cores:
+//
+//   centred form   SSR(b) = SSR(b0) - 2 d^T g + |X d|^2,  d = b - b0,  g = X^T (y - X b0)    (FP64 constants,
+//                  b0 = OLS computed at registration).  Same GEMM shape as y - X b, but its output is O(|d|),
+//                  so the FP32-equivalent product keeps Δlogπ accurate although logπ ~ -n/2.
+//   tensor cores   D[chain, row] = sum_k d[chain,k] X[row,k] with tcgen05.mma kind::tf32, M = 128 chains
+//                  (TMEM lane = chain), N = TILE_N data rows, accumulators in TMEM; FP32-equivalent accuracy by
+//                  the 3xTF32 split  d_hi X_hi + d_lo X_hi + d_hi X_lo  (X pre-split once, d split per proposal)
+//   TMA            X_hi / X_lo row tiles and the d_hi / d_lo chain tile arrive by cp.async.bulk.tensor (128-byte
+//                  swizzle, K-major) on mbarriers; a 3-role warp-specialised CTA per SM: TMA producer, MMA issuer,
+//                  4 epilogue warps
+//   fused epilogue tcgen05.ld the accumulator tile, square-and-sum along the data rows inside the thread that
+//                  owns the chain (no cross-lane reduction), FP32 per tile, FP64 across tiles; two TMEM
+//                  accumulator stages so the epilogue of tile t overlaps the MMAs of tile t+1
+//   determinism    fixed (chain tile, row chunk) -> CTA schedule, partial sums reduced in fixed order
+//
+// Around the GEMM, per generation and block: propose (Philox, archive gather, x', d split, d^T g) and
+// accept/select (tempered Metropolis in FP64, history, counters, Rhat accumulators, archive append) — the
+// same semantics as demcz_step.cuh (reference src/demcz.jl:167-203, 80-93; src/demcz_anneal.jl:142-178).
 #include "demcz_internal.h"
+#include "demcz_step.cuh"
+#include "demcz_tcgen05.cuh"
 
-extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t, int32_t, const double*, const double*)
+#include <cuda.h>
+#include <cmath>
+#include <cstring>
+#include <vector>
+
+using namespace demcz;
+
+#define CUL(c, call)                                                                                  \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess)                                                                        \
+            return demcz_fail((c), e_ == cudaErrorMemoryAllocation ? DEMCZ_ERR_OOM : DEMCZ_ERR_CUDA,  \
+                              "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_));   \
+    } while (0)
+
+struct demcz_linreg_state {
+    int64_t n = 0;
+    int p = 0, ppad = 0, ksteps = 0;
+    float *Xhi = nullptr, *Xlo = nullptr;          // [n][ppad] row-major, TF32-rounded hi / lo parts
+    double *d_b0 = nullptr, *d_g = nullptr;        // [64]
+    double ssr0 = 0.0;
+    int Npad = 0;                                  // chains rounded up to 128 (MMA M)
+    float *Dhi = nullptr, *Dlo = nullptr;          // [Npad][ppad] delta = x' - b0, split
+    float* Xprop = nullptr;                        // [d][ldx]
+    double *lin = nullptr, *partial = nullptr;     // [Npad], [R][Npad]
+    double* lp64 = nullptr;                        // [ldx] current log-objective
+    double* lphist64 = nullptr;                    // [G][N]
+    uint32_t* wacc = nullptr;                      // [ldx] accept word of the pending proposal
+    int tile_n = 0, tiles = 0, R = 0, tiles_per_chunk = 0;
+    int terms = 3;                                 // 3xTF32 (FP32-equivalent) or 1 (plain TF32; measurement only)
+    CUtensorMap tmXhi, tmXlo, tmDhi, tmDlo;
+    int sms = 148;
+    unsigned long long ssr_launches = 0;
+    std::vector<cudaEvent_t> ev;                   // profile=1: brackets of the SSR kernel launches of the last run
+    size_t ev_used = 0;
+};
+
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// registration-time kernels (FP64, one-off)
+// ------------------------------------------------------------------------------------------------
+// X col-major FP64 (n x p) -> row-major [n][ppad] TF32 hi / lo
+__global__ void split_x_kernel(const double* __restrict__ X, long long n, int p, int ppad, float* __restrict__ hi,
+                               float* __restrict__ lo)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    for (int k = 0; k < ppad; ++k) {
+        float h = 0.f, l = 0.f;
+        if (k < p) {
+            const double x = X[i + n * k];
+            h = tc::to_tf32((float)x);
+            l = tc::to_tf32((float)(x - (double)h));
+        }
+        hi[i * ppad + k] = h;
+        lo[i * ppad + k] = l;
+    }
+}
+
+// Per-block partial Gram matrices of [X | y]: out[block][a*(p+1) + b] = sum over the block's rows of col_a * col_b
+// (a, b <= p; column p is y).  The host adds the blocks in order: registration is bit-reproducible.
+__global__ void gram_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n, int p,
+                            long long rows_per_block, double* __restrict__ out)
+{
+    extern __shared__ double srow[];                  // [32 rows][p + 1]
+    const long long r0 = (long long)blockIdx.x * rows_per_block;
+    const long long r1 = min(n, r0 + rows_per_block);
+    const int P1 = p + 1;
+    const int npairs = P1 * P1;
+    double acc[20];                                    // up to ceil(65*65/256) = 17 pairs per thread
+#pragma unroll
+    for (int t = 0; t < 20; ++t) acc[t] = 0.0;
+    for (long long base = r0; base < r1; base += 32) {
+        const int nr = (int)min((long long)32, r1 - base);
+        __syncthreads();
+        for (int t = threadIdx.x; t < nr * P1; t += blockDim.x) {
+            const int k = t / nr, r = t - k * nr;      // consecutive threads -> consecutive rows (coalesced)
+            srow[r * P1 + k] = k < p ? X[base + r + n * k] : y[base + r];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int t = 0; t < 20; ++t) {
+            const int pr = threadIdx.x + t * blockDim.x;
+            if (pr < npairs) {
+                const int a = pr / P1, b = pr - a * P1;
+                double s = 0.0;
+                for (int r = 0; r < nr; ++r) s += srow[r * P1 + a] * srow[r * P1 + b];
+                acc[t] += s;
+            }
+        }
+    }
+#pragma unroll
+    for (int t = 0; t < 20; ++t) {
+        const int pr = threadIdx.x + t * blockDim.x;
+        if (pr < npairs) out[(size_t)blockIdx.x * npairs + pr] = acc[t];
+    }
+}
+
+// Per-block partials of g = X^T (y - X b0) and ssr0 = |y - X b0|^2: out[block][0..p) = g, out[block][p] = ssr0.
+// Each warp owns a row of the shared accumulator, the block's warps and then (on the host) the blocks are added
+// in a fixed order.
+__global__ void resid_kernel(const double* __restrict__ X, const double* __restrict__ y, long long n, int p,
+                             const double* __restrict__ b0, double* __restrict__ out)
+{
+    __shared__ double sb[64];
+    __shared__ double sg[8][65];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x < 64) sb[threadIdx.x] = threadIdx.x < p ? b0[threadIdx.x] : 0.0;
+    for (int t = threadIdx.x; t < 8 * 65; t += blockDim.x) (&sg[0][0])[t] = 0.0;
+    __syncthreads();
+    for (long long base = (long long)blockIdx.x * blockDim.x; base < n; base += (long long)gridDim.x * blockDim.x) {
+        const long long i = base + threadIdx.x;                  // warp-uniform trip count: the shuffles below need all lanes
+        const bool valid = i < n;
+        double r = valid ? y[i] : 0.0;
+        if (valid) for (int k = 0; k < p; ++k) r -= X[i + n * k] * sb[k];
+        for (int k = 0; k < p; ++k) {
+            double v = valid ? X[i + n * k] * r : 0.0;
+            v = warp_sum(v);
+            if (lane == 0) sg[warp][k] += v;
+        }
+        double v = warp_sum(r * r);
+        if (lane == 0) sg[warp][64] += v;
+    }
+    __syncthreads();
+    if (threadIdx.x <= p) {
+        const int k = threadIdx.x < p ? threadIdx.x : 64;
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sg[w][k];
+        out[(size_t)blockIdx.x * (p + 1) + threadIdx.x] = t;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-proposal kernels around the GEMM
+// ------------------------------------------------------------------------------------------------
+struct LinArgs {
+    // state
+    float* X; int N, ldx, d, ppad;
+    uint32_t chain_offset;
+    const float* Z; int ZS; uint32_t Mdraw, zstart, zcap;
+    long long gen, grel;          // absolute / context-relative generation of this proposal
+    PhiloxKeys keys;
+    int block, nblocks; uint32_t mask_lo, mask_hi; float cscale;
+    float eps[64];
+    __device__ bool in_block(int k) const { return (((k < 32 ? mask_lo : mask_hi) >> (k & 31)) & 1u) != 0; }
+    __device__ uint32_t group_mask(int k) const { return ((k < 32 ? mask_lo : mask_hi) >> (k & 24)) & 0xFFu; }   // 8-column jitter group of k
+    // outputs of propose
+    float* Xprop; uint32_t* wacc; float *Dhi, *Dlo; double* lin;
+    const double *b0, *g;
+    // trace
+    uint32_t *tr_r1, *tr_r2; float *tr_u, *tr_xprop;
+};
+
+// Philox draw, archive gather, x' = x + c (Z[r1]-Z[r2]) + eps .* z on the block (src/demcz.jl:174-188), then the
+// GEMM operands: d = x' - b0 split into TF32 hi / lo, and the FP64 linear term d^T g.
+// propose == false: d from the current state (initial log-objective, demcz_eval_logdensity).
+__global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
+{
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (chain >= a.N) return;
+    const uint32_t cid = a.chain_offset + (uint32_t)chain;
+    const uint32_t g_lo = (uint32_t)a.gen, g_hi = (uint32_t)((unsigned long long)a.gen >> 32);
+    const float *z1 = nullptr, *z2 = nullptr;
+    if (propose) {
+        const u32x4 w = philox4x32_10(cid, g_lo, (uint32_t)a.block << 16, g_hi, a.keys);
+        uint32_t r1, r2;
+        draw_pair(w.x, w.y, a.Mdraw, r1, r2);
+        if (a.tr_r1) {
+            const size_t o = ((size_t)(a.grel - 1) * a.nblocks + a.block) * a.N + chain;
+            a.tr_r1[o] = r1; a.tr_r2[o] = r2; a.tr_u[o] = uniform01(w.z);
+        }
+        r1 += a.zstart; if (r1 >= a.zcap) r1 -= a.zcap;
+        r2 += a.zstart; if (r2 >= a.zcap) r2 -= a.zcap;
+        z1 = a.Z + (size_t)r1 * a.ZS;
+        z2 = a.Z + (size_t)r2 * a.ZS;
+        a.wacc[chain] = w.z;
+    }
+    double lin = 0.0;
+    float2 zn[4];
+    for (int k = 0; k < a.d; ++k) {
+        const float x = a.X[(size_t)k * a.ldx + chain];
+        float xp = x;
+        if (propose) {
+            if ((k & 7) == 0 && a.group_mask(k) != 0) {
+                const u32x4 wn = philox4x32_10(cid, g_lo, ((uint32_t)a.block << 16) | (uint32_t)(1 + (k >> 3)), g_hi, a.keys);
+                zn[0] = box_muller16(wn.x); zn[1] = box_muller16(wn.y); zn[2] = box_muller16(wn.z); zn[3] = box_muller16(wn.w);
+            }
+            if (a.in_block(k)) {
+                const float2 zz = zn[(k & 7) >> 1];
+                const float z = (k & 1) ? zz.y : zz.x;
+                xp = fmaf(a.cscale, z1[k] - z2[k], fmaf(a.eps[k], z, x));
+            }
+            a.Xprop[(size_t)k * a.ldx + chain] = xp;
+            if (a.tr_xprop) a.tr_xprop[(((size_t)(a.grel - 1) * a.nblocks + a.block) * a.d + k) * a.N + chain] = xp;
+        }
+        const double dd = (double)xp - a.b0[k];
+        const float df = (float)dd;
+        const float hi = tc::to_tf32(df);
+        const float lo = tc::to_tf32(df - hi);
+        a.Dhi[(size_t)chain * a.ppad + k] = hi;
+        a.Dlo[(size_t)chain * a.ppad + k] = lo;
+        // the GEMM sees hi + lo; use the same value in the linear term
+        lin += ((double)hi + (double)lo) * a.g[k];
+    }
+    a.lin[chain] = lin;
+}
+
+struct AccArgs {
+    float* X; const float* Xprop; double* lp; const uint32_t* wacc;
+    int N, ldx, d, Npad, R;
+    const double *partial, *lin; double ssr0;
+    float T; int tempered;
+    long long grel; int block, nblocks; bool last_block;
+    // generation bookkeeping (last block only)
+    double* lp_gen0;              // [ldx] log-objective at the start of the generation
+    int* chain_changed; unsigned long long *win_changed, *accepted_total; int count_run, count_win;
+    float* hist; double* lphist;
+    float* Zw; int ZS; uint32_t append_row0, zcap, chain_offset;
+    float* S1; double* S2; const float* shift;
+    float* tr_lpprop; uint8_t* tr_acc;
+};
+
+// log-objective of the proposal from the GEMM partials, tempered Metropolis accept (src/demcz.jl:197-203,
+// src/demcz_anneal.jl:172-178) in FP64, select, and runchain!'s bookkeeping (src/demcz.jl:84-91).
+__global__ void linreg_accept_kernel(const AccArgs a)
+{
+    __shared__ unsigned int red[2];
+    __shared__ double red_s2[64];
+    if (threadIdx.x < 2) red[threadIdx.x] = 0;
+    if (threadIdx.x < 64) red_s2[threadIdx.x] = 0.0;
+    __syncthreads();
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = chain < a.N;
+    int acc_i = 0, win_i = 0;
+    if (active) {
+        double q = 0.0;
+        for (int r = 0; r < a.R; ++r) q += a.partial[(size_t)r * a.Npad + chain];
+        const double lpp = -0.5 * (a.ssr0 - 2.0 * a.lin[chain] + q);
+        const double lp = a.lp[chain];
+        if (a.block == 0 && a.lp_gen0) a.lp_gen0[chain] = lp;
+        const double logu = log((double)uniform01(a.wacc[chain]));
+        const double delta = lpp - lp;
+        const bool acc = a.tempered ? (logu * (double)a.T < delta) : (logu < delta);     // T = 0 -> greedy (Q4); NaN -> reject
+        if (a.tr_lpprop) {
+            const size_t o = ((size_t)(a.grel - 1) * a.nblocks + a.block) * a.N + chain;
+            a.tr_lpprop[o] = (float)lpp;
+            a.tr_acc[o] = acc ? 1 : 0;
+        }
+        double lpn = lp;
+        if (acc) {
+            for (int k = 0; k < a.d; ++k) a.X[(size_t)k * a.ldx + chain] = a.Xprop[(size_t)k * a.ldx + chain];
+            a.lp[chain] = lpp;
+            lpn = lpp;
+            acc_i = 1;
+        }
+        if (a.last_block) {
+            const bool changed = lpn != (a.lp_gen0 ? a.lp_gen0[chain] : lp);
+            if (changed && a.count_run) a.chain_changed[chain] += 1;
+            win_i = (changed && a.count_win) ? 1 : 0;
+            if (a.hist) {
+                for (int k = 0; k < a.d; ++k) a.hist[((size_t)(a.grel - 1) * a.d + k) * a.N + chain] = a.X[(size_t)k * a.ldx + chain];
+                a.lphist[(size_t)(a.grel - 1) * a.N + chain] = lpn;
+            }
+            if (a.Zw) {
+                uint32_t row = a.append_row0 + a.chain_offset + (uint32_t)chain;
+                if (row >= a.zcap) row -= a.zcap;
+                for (int k = 0; k < a.d; ++k) a.Zw[(size_t)row * a.ZS + k] = a.X[(size_t)k * a.ldx + chain];
+            }
+        }
+    }
+    if (a.last_block && a.S1) {                         // split-Rhat accumulators (src/utils.jl:2-20)
+        for (int k = 0; k < a.d; ++k) {
+            float t = 0.f;
+            if (active) {
+                t = a.X[(size_t)k * a.ldx + chain] - a.shift[k];
+                a.S1[(size_t)k * a.ldx + chain] += t;
+            }
+            const double v = warp_sum((double)t * (double)t);
+            if ((threadIdx.x & 31) == 0) atomicAdd(&red_s2[k], v);
+        }
+    }
+    const int wa = warp_sum(acc_i), ww = warp_sum(win_i);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[0], (unsigned)wa); atomicAdd(&red[1], (unsigned)ww); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (red[0]) atomicAdd(a.accepted_total, (unsigned long long)red[0]);
+        if (red[1]) atomicAdd(a.win_changed, (unsigned long long)red[1]);
+    }
+    if (a.last_block && a.S1 && threadIdx.x < a.d) atomicAdd(&a.S2[threadIdx.x], red_s2[threadIdx.x]);
+}
+
+__global__ void linreg_finish_eval_kernel(const double* __restrict__ partial, const double* __restrict__ lin, int n, int Npad,
+                                          int R, double ssr0, double* __restrict__ out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double q = 0.0;
+    for (int r = 0; r < R; ++r) q += partial[(size_t)r * Npad + i];
+    out[i] = -0.5 * (ssr0 - 2.0 * lin[i] + q);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the tensor-core kernel:  partial[rc][chain] = sum over the rows of chunk rc of (x_row . d_chain)^2
+// ------------------------------------------------------------------------------------------------
+constexpr int kSsrThreads = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+
+template <int KB, int TILE_N, int STAGES>
+struct SsrSmem {
+    static constexpr int A_BYTES = KB * 128 * 128;                 // one of d_hi / d_lo: KB k-blocks of [128 chains][128 B]
+    static constexpr int B_BYTES = KB * TILE_N * 128;              // one of X_hi / X_lo for one row tile
+    static constexpr int STAGE_BYTES = 2 * B_BYTES;
+    static constexpr int BAR_OFF = 2 * A_BYTES + STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;             // barriers + tmem holder + 1024-byte alignment slack
+};
+
+template <int KB, int TILE_N, int STAGES, int TERMS>
+__global__ void __launch_bounds__(kSsrThreads, 1)
+linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
+                  const __grid_constant__ CUtensorMap tmDhi, const __grid_constant__ CUtensorMap tmDlo, int ksteps, int tiles,
+                  int tiles_per_chunk, int CT, int units, int npad, double* __restrict__ partial)
+{
+    using L = SsrSmem<KB, TILE_N, STAGES>;
+    constexpr int ACC = 2;                                         // TMEM accumulator stages
+    constexpr uint32_t TMEM_COLS = ACC * TILE_N;                   // 512 or 256 (power of two)
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sA_hi = smem;
+    uint8_t* sA_lo = smem + L::A_BYTES;
+    uint8_t* sB = smem + 2 * L::A_BYTES;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
+    uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
+    uint64_t* a_full = bars + 2 * STAGES;  // chain tile landed
+    uint64_t* a_empty = a_full + 1;        // chain tile no longer read
+    uint64_t* tfull = a_empty + 1;         // [ACC] MMA -> epilogue
+    uint64_t* tempty = tfull + ACC;        // [ACC] epilogue -> MMA
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmXhi); tc::tma_prefetch_desc(&tmXlo); tc::tma_prefetch_desc(&tmDhi); tc::tma_prefetch_desc(&tmDlo);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
+        for (int s = 0; s < ACC; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0, aph = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int rc = u / CT, ct = u - rc * CT;
+                tc::mbar_wait(a_empty, aph ^ 1);
+                tc::mbar_arrive_expect_tx(a_full, 2 * L::A_BYTES);
+                for (int kb = 0; kb < KB; ++kb) {
+                    tc::tma_load_2d(sA_hi + kb * 128 * 128, &tmDhi, kb * 32, ct * 128, a_full);
+                    tc::tma_load_2d(sA_lo + kb * 128 * 128, &tmDlo, kb * 32, ct * 128, a_full);
+                }
+                aph ^= 1;
+                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    tc::mbar_wait(&empty[stage], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+                    uint8_t* bh = sB + stage * L::STAGE_BYTES;
+                    uint8_t* bl = bh + L::B_BYTES;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        tc::tma_load_2d(bh + kb * TILE_N * 128, &tmXhi, kb * 32, t * TILE_N, &full[stage]);
+                        tc::tma_load_2d(bl + kb * TILE_N * 128, &tmXlo, kb * 32, t * TILE_N, &full[stage]);
+                    }
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_tf32(128, TILE_N);
+            int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
+            const uint64_t a_hi0 = tc::make_sw128_kmajor_desc(sA_hi), a_lo0 = tc::make_sw128_kmajor_desc(sA_lo);
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int rc = u / CT;
+                tc::mbar_wait(a_full, aph);
+                aph ^= 1;
+                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    tc::mbar_wait(&tempty[as], tph ^ 1);
+                    tc::mbar_wait(&full[stage], ph);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
+                    const uint64_t b_hi0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
+                    const uint64_t b_lo0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES + L::B_BYTES);
+                    uint32_t accum = 0;
+                    // a k-step is 8 TF32 = 32 bytes inside the 128-byte swizzle row (descriptor start address + 2),
+                    // a k-block is the next [rows][128 B] panel.  Small cross terms first, hi*hi last.
+                    if (TERMS == 3) {
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            const uint64_t ao = (uint64_t)(((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4);
+                            const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
+                            tc::mma_tf32_ss(d_tmem, a_lo0 + ao, b_hi0 + bo, idesc, accum); accum = 1;
+                            tc::mma_tf32_ss(d_tmem, a_hi0 + ao, b_lo0 + bo, idesc, accum);
+                        }
+                    }
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        const uint64_t ao = (uint64_t)(((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4);
+                        const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
+                        tc::mma_tf32_ss(d_tmem, a_hi0 + ao, b_hi0 + bo, idesc, accum); accum = 1;
+                    }
+                    tc::mma_commit(&empty[stage]);             // X tile consumed -> producer may refill
+                    tc::mma_commit(&tfull[as]);                // accumulator ready -> epilogue
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                    if (++as == ACC) { as = 0; tph ^= 1; }
+                }
+                tc::mma_commit(a_empty);                       // chain tile no longer read
+            }
+        }
+    } else {
+        // ===================== epilogue: square-and-sum =====================
+        const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        int as = 0; uint32_t tph = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT, ct = u - rc * CT;
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            double accd = 0.0;
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&tfull[as], tph);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TILE_N);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 1
+                for (int c = 0; c < TILE_N; c += 64) {
+                    float v[32], w[32];
+                    tc::tmem_ld32(taddr + c, v);
+                    tc::tmem_ld32(taddr + c + 32, w);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
+                        s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        s0 = fmaf(w[j], w[j], s0); s1 = fmaf(w[j + 1], w[j + 1], s1);
+                        s2 = fmaf(w[j + 2], w[j + 2], s2); s3 = fmaf(w[j + 3], w[j + 3], s3);
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[as]);
+                accd += (double)((s0 + s1) + (s2 + s3));
+                if (++as == ACC) { as = 0; tph ^= 1; }
+            }
+            partial[(size_t)rc * npad + ct * 128 + quarter * 32 + lane] = accd;
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host helpers
+// ------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// row-major FP32 [rows][ppad] -> boxes of [box_rows][32 floats = 128 B], 128-byte swizzle, OOB rows read as zero
+int make_map(demcz_ctx* c, CUtensorMap* m, const float* base, uint64_t rows, int ppad, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return demcz_fail(c, DEMCZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)ppad, (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ppad * sizeof(float)};
+    const cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return demcz_fail(c, DEMCZ_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+    return DEMCZ_OK;
+}
+
+template <int KB, int TILE_N, int STAGES, int TERMS>
+cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& dhi, const CUtensorMap& dlo, int CT, int npad,
+                         double* partial)
+{
+    auto kern = linreg_ssr_kernel<KB, TILE_N, STAGES, TERMS>;
+    constexpr int smem = SsrSmem<KB, TILE_N, STAGES>::TOTAL;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    const int units = CT * s->R;
+    const int grid = std::min(units, s->sms);
+    kern<<<grid, kSsrThreads, smem, c->stream>>>(s->tmXhi, s->tmXlo, dhi, dlo, s->ksteps, s->tiles, s->tiles_per_chunk, CT, units,
+                                                 npad, partial);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& dhi, const CUtensorMap& dlo, int CT, int npad,
+                       double* partial)
+{
+    if (s->ppad == 32) {
+        if (s->terms == 3) return launch_ssr_t<1, 256, 3, 3>(c, s, dhi, dlo, CT, npad, partial);
+        return launch_ssr_t<1, 256, 3, 1>(c, s, dhi, dlo, CT, npad, partial);
+    }
+    if (s->terms == 3) return launch_ssr_t<2, 128, 2, 3>(c, s, dhi, dlo, CT, npad, partial);
+    return launch_ssr_t<2, 128, 2, 1>(c, s, dhi, dlo, CT, npad, partial);
+}
+
+inline int grid1(long long n, int t = 256) { return (int)((n + t - 1) / t); }
+
+}  // namespace
+
+// ------------------------------------------------------------------------------------------------
+// registration
+// ------------------------------------------------------------------------------------------------
+void demcz_linreg_free(demcz_ctx* c)
+{
+    demcz_linreg_state* s = c->linreg;
+    if (!s) return;
+    void* ptrs[] = {s->Xhi, s->Xlo, s->d_b0, s->d_g, s->Dhi, s->Dlo, s->Xprop, s->lin, s->partial, s->lp64, s->lphist64, s->wacc};
+    for (void* p : ptrs) if (p) cudaFree(p);
+    for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    delete s;
+    c->linreg = nullptr;
+}
+
+extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y)
 {
     if (!c) return DEMCZ_ERR_INVALID;
-    return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "linreg likelihood: not built yet");
+    if (c->sticky) return c->sticky;
+    if (cudaSetDevice(c->device) != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "cudaSetDevice(%d) failed", c->device);
+    if (!X || !y || n < 1 || p != c->o.d) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_likelihood_linreg: n=%lld p=%d, opts.d=%d", (long long)n, p, c->o.d);
+    if (p > DEMCZ_MAX_DIM_LINREG) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_likelihood_linreg: p=%d > %d", p, DEMCZ_MAX_DIM_LINREG);
+    if (n >= ((int64_t)1 << 31)) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_likelihood_linreg: n >= 2^31 rows");
+    int major = 0;
+    cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, c->device);
+    if (major != 10) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "the linreg likelihood needs tcgen05 (sm_100a); device has compute capability %d.x", major);
+    demcz_linreg_free(c);
+    demcz_linreg_state* s = new demcz_linreg_state();
+    c->linreg = s;
+    const demcz_opts& o = c->o;
+    s->n = n; s->p = p; s->ppad = p <= 32 ? 32 : 64; s->ksteps = (p + 7) / 8;
+    s->tile_n = s->ppad == 32 ? 256 : 128;
+    s->tiles = (int)((n + s->tile_n - 1) / s->tile_n);
+    s->R = std::max(1, std::min(37, s->tiles / 8));                 // row chunks: 37 | 148 keeps (chain tiles x chunks) balanced over the SMs
+    s->tiles_per_chunk = (s->tiles + s->R - 1) / s->R;
+    s->R = (s->tiles + s->tiles_per_chunk - 1) / s->tiles_per_chunk;
+    s->Npad = (o.N + 127) / 128 * 128;
+    if (const char* t = getenv("DEMCZ_LINREG_TERMS")) s->terms = atoi(t) == 1 ? 1 : 3;
+    cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, c->device);
+
+    const size_t np = (size_t)n * s->ppad;
+    double *dX = nullptr, *dy = nullptr, *dscr = nullptr;
+    CUL(c, cudaMalloc((void**)&s->Xhi, np * sizeof(float)));
+    CUL(c, cudaMalloc((void**)&s->Xlo, np * sizeof(float)));
+    CUL(c, cudaMalloc((void**)&s->d_b0, 64 * sizeof(double)));
+    CUL(c, cudaMalloc((void**)&s->d_g, 64 * sizeof(double)));
+    CUL(c, cudaMalloc((void**)&s->Dhi, (size_t)s->Npad * s->ppad * sizeof(float)));
+    CUL(c, cudaMalloc((void**)&s->Dlo, (size_t)s->Npad * s->ppad * sizeof(float)));
+    CUL(c, cudaMalloc((void**)&s->Xprop, (size_t)c->ldx * o.d * sizeof(float)));
+    CUL(c, cudaMalloc((void**)&s->lin, (size_t)s->Npad * sizeof(double)));
+    CUL(c, cudaMalloc((void**)&s->partial, (size_t)s->R * s->Npad * sizeof(double)));
+    CUL(c, cudaMalloc((void**)&s->lp64, (size_t)c->ldx * 2 * sizeof(double)));      // [lp | lp at generation start]
+    CUL(c, cudaMalloc((void**)&s->wacc, (size_t)c->ldx * sizeof(uint32_t)));
+    CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
+    CUL(c, cudaMemsetAsync(s->Dlo, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
+    CUL(c, cudaMemsetAsync(s->lp64, 0, (size_t)c->ldx * 2 * sizeof(double), c->stream));
+    if (o.store_chain && o.Ngeneration > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)o.Ngeneration * o.N * sizeof(double)));
+
+    // ---- upload (FP64, as the caller holds it), split, OLS reference point -------------------------
+    const int P1 = p + 1, npairs = P1 * P1;
+    const long long rpb = std::max<long long>(32, (n + 295) / 296);
+    const int gblocks = (int)((n + rpb - 1) / rpb);
+    const int rblocks = std::min(grid1(n), 592);
+    const size_t scr = std::max((size_t)gblocks * npairs, (size_t)rblocks * P1);
+    CUL(c, cudaMalloc((void**)&dX, (size_t)n * p * sizeof(double)));
+    cudaError_t e = cudaMalloc((void**)&dy, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dscr, scr * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dX, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    std::vector<double> hbuf(scr), G((size_t)npairs, 0.0);
+    if (e == cudaSuccess) {
+        split_x_kernel<<<grid1(n), 256, 0, c->stream>>>(dX, n, p, s->ppad, s->Xhi, s->Xlo);
+        gram_kernel<<<gblocks, 256, 32 * P1 * sizeof(double), c->stream>>>(dX, dy, n, p, rpb, dscr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hbuf.data(), dscr, (size_t)gblocks * npairs * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    std::vector<double> b0(64, 0.0);
+    if (e == cudaSuccess) {
+        for (int b = 0; b < gblocks; ++b)
+            for (int t = 0; t < npairs; ++t) G[t] += hbuf[(size_t)b * npairs + t];
+        // OLS by Cholesky of X^T X (host, FP64); a singular Gram matrix falls back to b0 = 0 (still exact, just
+        // less well conditioned)
+        std::vector<double> Lc((size_t)p * p, 0.0);
+        bool pd = true;
+        for (int j = 0; j < p && pd; ++j) {
+            double d = G[(size_t)j * P1 + j];
+            for (int k = 0; k < j; ++k) d -= Lc[(size_t)j * p + k] * Lc[(size_t)j * p + k];
+            if (!(d > 1e-12 * G[(size_t)j * P1 + j]) || !(d > 0.0)) { pd = false; break; }
+            const double ljj = sqrt(d);
+            Lc[(size_t)j * p + j] = ljj;
+            for (int i = j + 1; i < p; ++i) {
+                double t = G[(size_t)i * P1 + j];
+                for (int k = 0; k < j; ++k) t -= Lc[(size_t)i * p + k] * Lc[(size_t)j * p + k];
+                Lc[(size_t)i * p + j] = t / ljj;
+            }
+        }
+        if (pd) {
+            std::vector<double> z(p);
+            for (int i = 0; i < p; ++i) {
+                double t = G[(size_t)i * P1 + p];
+                for (int k = 0; k < i; ++k) t -= Lc[(size_t)i * p + k] * z[k];
+                z[i] = t / Lc[(size_t)i * p + i];
+            }
+            for (int i = p - 1; i >= 0; --i) {
+                double t = z[i];
+                for (int k = i + 1; k < p; ++k) t -= Lc[(size_t)k * p + i] * b0[k];
+                b0[i] = t / Lc[(size_t)i * p + i];
+            }
+        }
+        e = cudaMemcpyAsync(s->d_b0, b0.data(), 64 * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    }
+    if (e == cudaSuccess) {
+        resid_kernel<<<rblocks, 256, 0, c->stream>>>(dX, dy, n, p, s->d_b0, dscr);
+        e = cudaGetLastError();
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(hbuf.data(), dscr, (size_t)rblocks * P1 * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    if (e == cudaSuccess) {
+        std::vector<double> g(64, 0.0);
+        double ssr0 = 0.0;
+        for (int b = 0; b < rblocks; ++b) {
+            for (int k = 0; k < p; ++k) g[k] += hbuf[(size_t)b * P1 + k];
+            ssr0 += hbuf[(size_t)b * P1 + p];
+        }
+        s->ssr0 = ssr0;
+        e = cudaMemcpy(s->d_g, g.data(), 64 * sizeof(double), cudaMemcpyHostToDevice);
+    }
+    cudaFree(dX);
+    if (dy) cudaFree(dy);
+    if (dscr) cudaFree(dscr);
+    CUL(c, e);
+
+    int rc = make_map(c, &s->tmXhi, s->Xhi, (uint64_t)n, s->ppad, s->tile_n);
+    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmXlo, s->Xlo, (uint64_t)n, s->ppad, s->tile_n);
+    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmDhi, s->Dhi, (uint64_t)s->Npad, s->ppad, 128);
+    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmDlo, s->Dlo, (uint64_t)s->Npad, s->ppad, 128);
+    if (rc != DEMCZ_OK) return rc;
+    c->lik_kind = DEMCZ_LIK_LINREG;
+    c->state_lp_valid = false;
+    return DEMCZ_OK;
 }
-int demcz_linreg_eval(demcz_ctx* c, const float*, int, int, float*) { return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "linreg: not built yet"); }
-int demcz_linreg_generations(demcz_ctx* c, int64_t, int, bool) { return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "linreg: not built yet"); }
-void demcz_linreg_free(demcz_ctx*) {}
+
+// ------------------------------------------------------------------------------------------------
+// batched evaluation: map(logobj, rows) (src/demcz.jl:17)
+// ------------------------------------------------------------------------------------------------
+int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_dev)
+{
+    demcz_linreg_state* s = c->linreg;
+    if (!s) return demcz_fail(c, DEMCZ_ERR_INVALID, "linreg likelihood not set");
+    const bool own_state = (out_dev == nullptr);           // the context's own chains -> lp64
+    const int npad = (n + 127) / 128 * 128;
+    float *dhi = s->Dhi, *dlo = s->Dlo; double *lin = s->lin, *partial = s->partial;
+    CUtensorMap mh = s->tmDhi, ml = s->tmDlo;
+    void* tmp = nullptr;
+    if (npad > s->Npad) {                                   // evaluation of more points than chains: temporaries
+        const size_t fb = (size_t)npad * s->ppad * sizeof(float);
+        const size_t total = 2 * fb + (size_t)npad * sizeof(double) * (1 + s->R);
+        CUL(c, cudaMalloc(&tmp, total));
+        CUL(c, cudaMemsetAsync(tmp, 0, total, c->stream));
+        dhi = (float*)tmp; dlo = (float*)((char*)tmp + fb);
+        lin = (double*)((char*)tmp + 2 * fb); partial = lin + npad;
+        int rc = make_map(c, &mh, dhi, (uint64_t)npad, s->ppad, 128);
+        if (rc == DEMCZ_OK) rc = make_map(c, &ml, dlo, (uint64_t)npad, s->ppad, 128);
+        if (rc != DEMCZ_OK) { cudaFree(tmp); return rc; }
+    }
+    LinArgs a;
+    memset(&a, 0, sizeof a);
+    a.X = const_cast<float*>(X); a.N = n; a.ldx = ldx; a.d = c->o.d; a.ppad = s->ppad;
+    a.Dhi = dhi; a.Dlo = dlo; a.lin = lin; a.b0 = s->d_b0; a.g = s->d_g;
+    linreg_prepare_kernel<<<grid1(n, 128), 128, 0, c->stream>>>(a, false);
+    cudaError_t e = cudaGetLastError();
+    const int use_npad = npad > s->Npad ? npad : s->Npad;
+    if (e == cudaSuccess) e = launch_ssr(c, s, mh, ml, npad / 128, use_npad, partial);
+    if (e == cudaSuccess) {
+        linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R, s->ssr0, own_state ? s->lp64 : out_dev);
+        e = cudaGetLastError();
+    }
+    s->ssr_launches++;
+    if (tmp) { if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream); cudaFree(tmp); }
+    CUL(c, e);
+    return DEMCZ_OK;
+}
+
+double* demcz_linreg_lp(demcz_ctx* c) { return c->linreg ? c->linreg->lp64 : nullptr; }
+double* demcz_linreg_lphist(demcz_ctx* c) { return c->linreg ? c->linreg->lphist64 : nullptr; }
+unsigned long long demcz_linreg_launches(demcz_ctx* c) { return c->linreg ? c->linreg->ssr_launches : 0; }
+
+double demcz_linreg_profile_ms(demcz_ctx* c, long long* launches)
+{
+    demcz_linreg_state* s = c->linreg;
+    double tot = 0.0;
+    if (launches) *launches = 0;
+    if (!s) return 0.0;
+    for (size_t i = 0; i + 1 < s->ev_used; i += 2) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, s->ev[i], s->ev[i + 1]) == cudaSuccess) tot += t;
+    }
+    if (launches) *launches = (long long)(s->ev_used / 2);
+    s->ev_used = 0;
+    return tot;
+}
+
+// ------------------------------------------------------------------------------------------------
+// generations [g, g + n_gens) of this context (0-based g), archive frozen; append after the last one if asked
+// ------------------------------------------------------------------------------------------------
+int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half)
+{
+    demcz_linreg_state* s = c->linreg;
+    if (!s) return demcz_fail(c, DEMCZ_ERR_INVALID, "linreg likelihood not set");
+    const demcz_opts& o = c->o;
+    const int CT = s->Npad / 128;
+    for (int gi = 0; gi < n_gens; ++gi) {
+        const int64_t grel = g + gi + 1;
+        for (int b = 0; b < o.Nblocks; ++b) {
+            LinArgs a;
+            memset(&a, 0, sizeof a);
+            a.X = c->dX; a.N = o.N; a.ldx = c->ldx; a.d = o.d; a.ppad = s->ppad;
+            a.chain_offset = (uint32_t)o.chain_offset;
+            a.Z = c->dZ; a.ZS = c->ZS;
+            a.Mdraw = (uint32_t)std::min<int64_t>(c->M, c->zcap);
+            a.zcap = (uint32_t)c->zcap;
+            a.zstart = c->M > c->zcap ? (uint32_t)(c->M % c->zcap) : 0u;
+            a.gen = o.gen_offset + grel; a.grel = grel;
+            a.keys = c->keys;
+            a.block = b; a.nblocks = o.Nblocks;
+            uint64_t mask = 0;
+            for (int t = c->block_ptr[b]; t < c->block_ptr[b + 1]; ++t) mask |= (uint64_t)1 << c->block_idx[t];
+            a.mask_lo = (uint32_t)mask; a.mask_hi = (uint32_t)(mask >> 32);
+            const int blocklen = c->block_ptr[b + 1] - c->block_ptr[b];
+            a.cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
+            for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
+            a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
+            a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
+            if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
+            linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true);
+            CUL(c, cudaGetLastError());
+
+            if (o.profile) {
+                while (s->ev.size() < s->ev_used + 2) { cudaEvent_t ev; CUL(c, cudaEventCreate(&ev)); s->ev.push_back(ev); }
+                CUL(c, cudaEventRecord(s->ev[s->ev_used], c->stream));
+            }
+            CUL(c, launch_ssr(c, s, s->tmDhi, s->tmDlo, CT, s->Npad, s->partial));
+            if (o.profile) { CUL(c, cudaEventRecord(s->ev[s->ev_used + 1], c->stream)); s->ev_used += 2; }
+            s->ssr_launches++;
+
+            AccArgs q;
+            memset(&q, 0, sizeof q);
+            q.X = c->dX; q.Xprop = s->Xprop; q.lp = s->lp64; q.wacc = s->wacc;
+            q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R;
+            q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0;
+            q.tempered = o.anneal ? 1 : 0;
+            q.T = o.anneal ? c->hT[(size_t)grel - 1] : 1.f;
+            q.grel = grel; q.block = b; q.nblocks = o.Nblocks; q.last_block = (b == o.Nblocks - 1);
+            q.lp_gen0 = o.Nblocks > 1 ? s->lp64 + c->ldx : nullptr;
+            q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
+            q.count_run = (grel != 1) ? 1 : 0;
+            q.count_win = (o.anneal && o.adapt && (grel - 1) % o.adapt_every == 0) ? 0 : 1;
+            q.hist = c->dhist; q.lphist = s->lphist64;
+            const bool do_append = append && gi == n_gens - 1;
+            q.Zw = do_append ? c->dZ : nullptr; q.ZS = c->ZS;
+            q.append_row0 = (uint32_t)(c->M % c->zcap); q.zcap = (uint32_t)c->zcap; q.chain_offset = (uint32_t)o.chain_offset;
+            if (acc) { q.S1 = c->dS1[half]; q.S2 = c->dS2 + (size_t)half * o.d; q.shift = c->dshift; }
+            q.tr_lpprop = c->tr_lpprop; q.tr_acc = c->tr_acc;
+            linreg_accept_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(q);
+            CUL(c, cudaGetLastError());
+        }
+    }
+    return DEMCZ_OK;
+}
