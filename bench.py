@@ -231,10 +231,16 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c4")
+    ap.add_argument("--workload", default=None,
+                    help="c2 (default: BASELINE configs[1], linreg on tcgen05), c4, c3, c1, c5; without this flag the line also "
+                         "carries a short run of c4 (the 1M-chain MvNormal scaling config) under the key 'also'")
+    ap.add_argument("--no-also", action="store_true")
     ap.add_argument("--gens-per-step", type=int, default=0)
     ap.add_argument("--chains-per-gpu", type=int, default=0)
     ap.add_argument("--archive-rows", type=int, default=0)
+    ap.add_argument("--sync", default="overlap", choices=["strict", "overlap"],
+                    help="strict: appended rows drawable at once (bit-identical to 1 GPU); overlap: one K-block later, exchange hidden under compute")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="p2p: own push kernel over peer-mapped archives; nccl: ncclAllGather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -244,20 +250,30 @@ def main():
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
     local_rank = int(os.environ.get("LOCAL_RANK", 0))
-    w = workload(args.workload, args.chains_per_gpu, args.archive_rows)
-    d, K = w["d"], w["K"]
-    gps = args.gens_per_step or (10 if w["kind"] == "linreg" else 100)
-    cfg = dict(workload=w["name"], chains_per_gpu=w["chains_per_gpu"], chains_total=w["chains_per_gpu"] * max(world, 1),
+    primary = args.workload or "c2"
+
+    def make_cfg(wname):
+        w = workload(wname, args.chains_per_gpu, args.archive_rows)
+        gps = args.gens_per_step or (10 if w["kind"] == "linreg" else 100)
+        return w, gps, _cfg(w, gps)
+
+    def _cfg(w, gps):
+        K = w["K"]
+        return dict(workload=w["name"], chains_per_gpu=w["chains_per_gpu"], chains_total=w["chains_per_gpu"] * max(world, 1),
                generations_per_step=gps, K=K, Nblocks=len(w["blocks"]), archive_rows_initial=w["archive_rows"],
                archive="replicated, ring buffer",
                l2=("X_hi + X_lo (2 x 4 n p bytes) > L2 (126 MB) and re-streamed every generation; no flush needed" if w["kind"] == "linreg"
                    else "archive > L2 (126 MB): random gathers miss L2; no flush needed"),
-               parallelism=f"chains sharded x{world}, NCCL all-gather of appended rows every K generations")
+               sync_mode=args.sync,
+               parallelism=(f"chains sharded x{world}; appended rows exchanged every K generations by "
+                            + ("our push kernel into peer-mapped archive replicas (NVLink), published by flag words" if args.exchange == "p2p" else "ncclAllGather")
+                            + (", on a side stream under the next K-block" if args.sync == "overlap" else ", on the compute stream")))
 
     # ---------------------------------------------------------------- reference arm (CPU) -------
     if args.impl == "reference":
         if rank != 0:
             return 0
+        w, gps, cfg = make_cfg(primary)
         threads = os.cpu_count() or 1
         prepare_data(w)
         chains, g0 = cpu_sample_size(w, threads)
@@ -312,136 +328,152 @@ def main():
         tdist.all_reduce(t, op=tdist.ReduceOp.SUM)
         return float(t.item())
 
-    N_local = w["chains_per_gpu"]
-    N_global = N_local * world
-    total_steps = args.warmup + args.steps + (0 if args.no_e2e else args.warmup + args.steps) + 1
-    G_total = total_steps * gps
-    M0 = w["archive_rows"]
-    cap = max(M0 + N_global * 16, 64 << 20) if args.workload != "c1" else 0
-    if cap:
-        cap = (cap + N_global - 1) // N_global * N_global            # append segments never straddle the ring end
-    prepare_data(w)
-    if w["kind"] == "linreg":
-        logobj = DEMC.LinRegLoglik(w["X"], w["y"])
-        cap = 0
-    else:
-        logobj = (DEMC.QuadraticLogobj(w["mu"]) if w["kind"] == "quad" else DEMC.MvNormalLogpdf(w["mu"], w["Sigma"]))
-    Z0 = make_archive(w, M0)
-    s = ddist.make_sharded_sampler(logobj, d, N_global=N_global, rank=rank, world=world, device=local_rank, K=K,
-                                   Ngeneration=G_total, blockindex=w["blocks"], eps_scale=1e-5 * np.ones(d), γ=w["gamma"],
-                                   anneal=w["anneal"], T0=2.0, TN=1e-4, autostop=w["autostop"], autostop_every=1000,
-                                   autostop_Rhat=0.0, adapt=False, seed=31953150, store_chain=False, archive_capacity=cap)
-    s.set_archive(Z0)
-    del Z0
+    def measure(wname, steps, warmup, do_e2e, do_cpu):
+        w, gps, cfg = make_cfg(wname)
+        d, K = w["d"], w["K"]
+        N_local = w["chains_per_gpu"]
+        N_global = N_local * world
+        total_steps = warmup + steps + (warmup + steps if do_e2e else 0) + 1
+        G_total = total_steps * gps
+        M0 = w["archive_rows"]
+        cap = max(M0 + N_global * 16, 64 << 20) if wname != "c1" else 0
+        if cap:
+            cap = (cap + N_global - 1) // N_global * N_global            # append segments never straddle the ring end
+        prepare_data(w)
+        if w["kind"] == "linreg":
+            logobj = DEMC.LinRegLoglik(w["X"], w["y"])
+            cap = 0
+        else:
+            logobj = (DEMC.QuadraticLogobj(w["mu"]) if w["kind"] == "quad" else DEMC.MvNormalLogpdf(w["mu"], w["Sigma"]))
+        Z0 = make_archive(w, M0)
+        s = ddist.make_sharded_sampler(logobj, d, N_global=N_global, rank=rank, world=world, device=local_rank, K=K,
+                                       Ngeneration=G_total, blockindex=w["blocks"], eps_scale=1e-5 * np.ones(d), γ=w["gamma"],
+                                       anneal=w["anneal"], T0=2.0, TN=1e-4, autostop=w["autostop"], autostop_every=1000,
+                                       autostop_Rhat=0.0, adapt=False, seed=31953150, store_chain=False, archive_capacity=cap,
+                                       sync_mode=args.sync)
+        s.set_archive(Z0)
+        del Z0
+        if world > 1 and args.exchange == "p2p":
+            ddist.open_peer_archives(s, rank=rank, world=world, device=local_rank)
 
-    for _ in range(args.warmup):
-        s.run(gps)
-
-    clocks = ClockSampler(local_rank)
-    barrier()
-    if rank == 0:
-        clocks.start()
-    t0 = time.perf_counter()
-    info = s.run(gps * args.steps)              # one call: CUDA events on the library's stream bracket exactly K steps
-    barrier()
-    wall_ms = 1e3 * (time.perf_counter() - t0)
-    clk = clocks.stop() if rank == 0 else None
-    dev_ms = max_over_ranks(info["device_ms"])
-    wall_ms = max_over_ranks(wall_ms)
-    launches = int(sum_over_ranks(info["step_launches"]))
-    updates = N_global * gps * args.steps
-    value = updates / (dev_ms * 1e-3)
-    acc_frac = None
-
-    # ---- e2e: public Sampler API, host (pinned) population in and out every step ------------------
-    e2e = None
-    if not args.no_e2e:
-        Xh = torch.empty((d, N_local), dtype=torch.float64).pin_memory().numpy().T      # N x d, Fortran order
-        lph = torch.empty(N_local, dtype=torch.float64).pin_memory().numpy()
-        Xo = torch.empty((d, N_local), dtype=torch.float64).pin_memory().numpy().T
-        lpo = torch.empty(N_local, dtype=torch.float64).pin_memory().numpy()
-        dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
-        s._check(s.lib.demcz_get_state(s.ctx, dp(Xh), dp(lph)))
-
-        def e2e_step():
-            s._check(s.lib.demcz_set_state(s.ctx, dp(Xh), dp(lph)))                       # H2D: population + log-objective
+        for _ in range(warmup):
             s.run(gps)
-            s._check(s.lib.demcz_get_state(s.ctx, dp(Xo), dp(lpo)))                       # D2H: new population + log-objective
-            Xh[...] = Xo
-            lph[...] = lpo
 
-        for _ in range(args.warmup):
-            e2e_step()
+        clocks = ClockSampler(local_rank)
         barrier()
+        if rank == 0:
+            clocks.start()
         t0 = time.perf_counter()
-        for _ in range(args.steps):
-            e2e_step()
+        info = s.run(gps * steps)              # one call: CUDA events on the library's stream bracket exactly K steps
         barrier()
-        e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
-        nbytes = N_global * (d + 1) * 8
-        e2e = dict(value=updates / (e2e_ms * 1e-3), unit="chain-updates/s", h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
-                   ms_per_step=e2e_ms / args.steps,
-                   api="Sampler.set_state(host X, logp) -> run(generations_per_step) -> get_state() each step; archive resident")
+        wall_ms = 1e3 * (time.perf_counter() - t0)
+        clk = clocks.stop() if rank == 0 else None
+        dev_ms = max_over_ranks(info["device_ms"])
+        wall_ms = max_over_ranks(wall_ms)
+        launches = int(sum_over_ranks(info["step_launches"]))
+        updates = N_global * gps * steps
+        value = updates / (dev_ms * 1e-3)
+        acc_frac = None
 
-    # ---- roofline of the step kernel: per-launch CUDA-event durations, live ---------------------------
-    s.set_profile(True)
-    pinfo = s.run(gps)
-    s.set_profile(False)
-    roof = None
-    if pinfo["step_launches"] > 0 and w["kind"] == "linreg":
-        n_l = pinfo["step_launches"]
-        avg_ms = pinfo["step_kernel_ms"] / n_l
-        flops = 2.0 * w["n"] * d * N_local                       # FP32-equivalent flops of X (n x p) . B^T (p x N)
-        achieved = flops / (avg_ms * 1e-3) / 1e12
-        tf32 = measure_tf32_peak()
-        bf16 = None
-        try:
-            bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
-        except Exception:
-            pass
-        roof = dict(bound="tensor", kernel="linreg_ssr_kernel (tcgen05 kind::tf32, 3xTF32)", achieved=achieved, peak=tf32 / 3.0,
-                    unit="TFLOP/s", frac=achieved / (tf32 / 3.0), traffic=None,
-                    peak_source=f"TF32 dense measured live with torch.matmul 8192^3 = {tf32:.0f} TFLOP/s, / 3 for the 3xTF32 split "
-                                f"(MEASURED_PEAKS.json bf16_tflops = {bf16})",
-                    tensor_issued_tflops=3 * achieved, tensor_frac_of_tf32_peak=3 * achieved / tf32, launch_us=avg_ms * 1e3,
-                    flops_per_launch=flops, kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
-        acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
-    elif pinfo["step_launches"] > 0:
-        n_l = pinfo["step_launches"]
-        avg_ms = pinfo["step_kernel_ms"] / n_l
-        G_f = gps / n_l
-        bpu = algorithmic_bytes_per_update(d, K, G_f)
-        bytes_per_launch = N_local * G_f * bpu
-        achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
-        peak, which = 6650.0, "fallback"
-        try:
-            peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); which = "measured"
-        except Exception:
-            pass
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload)
-        except Exception:
-            pass
-        roof = dict(bound="hbm", kernel="demcz_step_mvn_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
-                    peak_source=f"MEASURED_PEAKS.json hbm_gbs ({which})", traffic=traffic, launch_us=avg_ms * 1e3,
-                    generations_per_launch=G_f, algorithmic_bytes_per_update=bpu, bytes_per_launch=bytes_per_launch,
-                    kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
-        acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
-    s.close()
+        # ---- e2e: public Sampler API, host (pinned) population in and out every step ------------------
+        e2e = None
+        if do_e2e:
+            Xh = torch.empty((d, N_local), dtype=torch.float64).pin_memory().numpy().T      # N x d, Fortran order
+            lph = torch.empty(N_local, dtype=torch.float64).pin_memory().numpy()
+            Xo = torch.empty((d, N_local), dtype=torch.float64).pin_memory().numpy().T
+            lpo = torch.empty(N_local, dtype=torch.float64).pin_memory().numpy()
+            dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
+            s._check(s.lib.demcz_get_state(s.ctx, dp(Xh), dp(lph)))
 
-    cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_baseline(w)
+            def e2e_step():
+                s._check(s.lib.demcz_set_state(s.ctx, dp(Xh), dp(lph)))                       # H2D: population + log-objective
+                s.run(gps)
+                s._check(s.lib.demcz_get_state(s.ctx, dp(Xo), dp(lpo)))                       # D2H: new population + log-objective
+                Xh[...] = Xo
+                lph[...] = lpo
+
+            for _ in range(warmup):
+                e2e_step()
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(steps):
+                e2e_step()
+            barrier()
+            e2e_ms = max_over_ranks(1e3 * (time.perf_counter() - t0))
+            nbytes = N_global * (d + 1) * 8
+            e2e = dict(value=updates / (e2e_ms * 1e-3), unit="chain-updates/s", h2d_bytes_per_step=nbytes, d2h_bytes_per_step=nbytes,
+                       ms_per_step=e2e_ms / steps,
+                       api="Sampler.set_state(host X, logp) -> run(generations_per_step) -> get_state() each step; archive resident")
+
+        # ---- roofline of the step kernel: per-launch CUDA-event durations, live ---------------------------
+        s.set_profile(True)
+        pinfo = s.run(gps)
+        s.set_profile(False)
+        roof = None
+        if pinfo["step_launches"] > 0 and w["kind"] == "linreg":
+            n_l = pinfo["step_launches"]
+            avg_ms = pinfo["step_kernel_ms"] / n_l
+            flops = 2.0 * w["n"] * d * N_local                       # FP32-equivalent flops of X (n x p) . B^T (p x N)
+            achieved = flops / (avg_ms * 1e-3) / 1e12
+            tf32 = measure_tf32_peak()
+            bf16 = None
+            try:
+                bf16 = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops"])
+            except Exception:
+                pass
+            roof = dict(bound="tensor", kernel="linreg_ssr_kernel (tcgen05 kind::tf32, 3xTF32)", achieved=achieved, peak=tf32 / 3.0,
+                        unit="TFLOP/s", frac=achieved / (tf32 / 3.0), traffic=None,
+                        peak_source=f"TF32 dense measured live with torch.matmul 8192^3 = {tf32:.0f} TFLOP/s, / 3 for the 3xTF32 split "
+                                    f"(MEASURED_PEAKS.json bf16_tflops = {bf16})",
+                        tensor_issued_tflops=3 * achieved, tensor_frac_of_tf32_peak=3 * achieved / tf32, launch_us=avg_ms * 1e3,
+                        flops_per_launch=flops, kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
+            acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
+        elif pinfo["step_launches"] > 0:
+            n_l = pinfo["step_launches"]
+            avg_ms = pinfo["step_kernel_ms"] / n_l
+            G_f = gps / n_l
+            bpu = algorithmic_bytes_per_update(d, K, G_f)
+            bytes_per_launch = N_local * G_f * bpu
+            achieved = bytes_per_launch / (avg_ms * 1e-3) / 1e9
+            peak, which = 6650.0, "fallback"
+            try:
+                peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]); which = "measured"
+            except Exception:
+                pass
+            traffic = None
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(wname)
+            except Exception:
+                pass
+            roof = dict(bound="hbm", kernel="demcz_step_mvn_kernel", achieved=achieved, peak=peak, unit="GB/s", frac=achieved / peak,
+                        peak_source=f"MEASURED_PEAKS.json hbm_gbs ({which})", traffic=traffic, launch_us=avg_ms * 1e3,
+                        generations_per_launch=G_f, algorithmic_bytes_per_update=bpu, bytes_per_launch=bytes_per_launch,
+                        kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
+            acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
+        if roof is not None and pinfo.get("exchanges"):
+            roof["exchange_us"] = 1e3 * pinfo["exchange_ms"] / pinfo["exchanges"]      # per K-block, this rank (device time of the push / all-gather)
+        s.close()
+
+        cpu = None
+        if rank == 0 and world == 1 and do_cpu:
+            cpu = cpu_baseline(w)
+        return dict(metric="chain-updates/s", value=value, unit="chain-updates/s", n_gpus=world, steps=steps, warmup=warmup,
+                    ms_per_step=dev_ms / steps, wall_ms_per_step=wall_ms / steps, higher_is_better=True, scaling="weak",
+                    vs_baseline=None,
+                    dtype="f32 (linreg: 3xTF32 products, FP32 accumulate, FP64 sums)" if w["kind"] == "linreg" else "f32",
+                    data="synthetic", config=cfg, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
+                    accepted_fraction=acc_frac, proposals_per_s=value * len(w["blocks"]))
+
+    res = measure(primary, args.steps, args.warmup, not args.no_e2e, not args.no_cpu_baseline)
+    if args.workload is None and not args.no_also:
+        # the 1M-chain MvNormal configuration (BASELINE configs[3]; 131072 chains per GPU), short run, same rules
+        a = measure("c4", max(3, args.steps // 2), 3, False, False)
+        res["also"] = {"c4": {k: a[k] for k in ("value", "unit", "ms_per_step", "config", "roofline", "gpu_launches", "accepted_fraction")}}
     if world > 1:
         barrier()
         tdist.destroy_process_group()
     if rank == 0:
-        print(json.dumps(dict(metric="chain-updates/s", value=value, unit="chain-updates/s", n_gpus=world, steps=args.steps,
-                              warmup=args.warmup, ms_per_step=dev_ms / args.steps, wall_ms_per_step=wall_ms / args.steps,
-                              higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32 (linreg: 3xTF32 products, FP32 accumulate, FP64 sums)" if w["kind"] == "linreg" else "f32",
-                              data="synthetic", config=cfg, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
-                              accepted_fraction=acc_frac, proposals_per_s=value * len(w["blocks"]))))
+        print(json.dumps(res))
     return 0
 
 

@@ -40,7 +40,7 @@ class RunInfo(C.Structure):
         ("generations_done", C.c_int64), ("generations_total", C.c_int64), ("stopped_by_rhat", C.c_int32),
         ("rhat_valid", C.c_int32), ("rhat_max", C.c_double), ("final_gamma", C.c_double), ("M", C.c_int64),
         ("proposals", C.c_int64), ("accepted", C.c_int64), ("step_launches", C.c_int64),
-        ("step_kernel_ms", C.c_double), ("device_ms", C.c_double),
+        ("step_kernel_ms", C.c_double), ("device_ms", C.c_double), ("exchange_ms", C.c_double), ("exchanges", C.c_int64),
     ]
 
 
@@ -48,7 +48,7 @@ EXPORTS = [
     "demcz_version", "demcz_create", "demcz_destroy", "demcz_last_error", "demcz_set_likelihood_mvnormal",
     "demcz_set_likelihood_linreg", "demcz_set_archive", "demcz_set_state", "demcz_set_temperature_table",
     "demcz_run", "demcz_set_profile", "demcz_get_chain", "demcz_get_state", "demcz_get_archive", "demcz_get_moments", "demcz_get_rhat",
-    "demcz_get_accept_counts", "demcz_eval_logdensity", "demcz_get_trace", "demcz_comm_unique_id", "demcz_comm_init",
+    "demcz_get_accept_counts", "demcz_eval_logdensity", "demcz_get_trace", "demcz_comm_unique_id", "demcz_comm_init", "demcz_comm_peer_info", "demcz_comm_open_peers",
 ]
 
 _lib = None
@@ -87,5 +87,7 @@ def load():
     lib.demcz_get_trace.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.demcz_comm_unique_id.argtypes = [C.POINTER(C.c_uint8)]
     lib.demcz_comm_init.argtypes = [vp, C.POINTER(C.c_uint8)]
+    lib.demcz_comm_peer_info.argtypes = [vp, C.POINTER(C.c_uint8)]
+    lib.demcz_comm_open_peers.argtypes = [vp, C.POINTER(C.c_uint8)]
     _lib = lib
     return lib

@@ -227,6 +227,15 @@ class Sampler:
         buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
         self._check(self.lib.demcz_comm_init(self.ctx, buf))
 
+    def peer_info(self) -> bytes:
+        buf = (C.c_uint8 * 128)()
+        self._check(self.lib.demcz_comm_peer_info(self.ctx, buf))
+        return bytes(buf)
+
+    def open_peers(self, infos: bytes):
+        buf = (C.c_uint8 * len(infos)).from_buffer_copy(infos)
+        self._check(self.lib.demcz_comm_open_peers(self.ctx, buf))
+
     # -- run ---------------------------------------------------------------------------------
     def run(self, max_generations=0):
         info = _lib.RunInfo()

@@ -60,19 +60,35 @@ struct demcz_ctx {
     bool rhat_valid = false;
 
     std::vector<cudaEvent_t> ev_pool;
+    std::vector<cudaEvent_t> ev_xchg;            // profile=1: brackets of the exchanges of the current run
+    size_t xchg_used = 0;
     cudaEvent_t ev_run[2] = {nullptr, nullptr};
 
-    // NCCL (dlopen'ed; demcz_comm.cu)
+    // NCCL (dlopen'ed; demcz_comm.cu) and the peer-to-peer exchange
     void* comm = nullptr;
+    void* comm2 = nullptr;                       // communicator of the side stream
+    cudaStream_t comm_stream = nullptr;
+    cudaEvent_t ev_app[2] = {nullptr, nullptr};  // compute -> side: segment written locally
+    cudaEvent_t ev_vis[2] = {nullptr, nullptr};  // side -> compute: segment complete on every rank
+    unsigned long long* d_barrier = nullptr;
+    float* peerZ[8] = {nullptr};
+    bool peer_ipc[8] = {false};
+    bool peers_open = false;
+    int64_t appends = 0;                         // archive appends so far (overlap mode: visibility lags by one)
+    int64_t vis_waited = 0;
+    int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
 
     std::string err;
     int sticky = 0;
 };
 
 int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
+int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart);
+int demcz_archive_appended(demcz_ctx* c);
 
 // demcz_comm.cu — no-ops when world == 1
-int demcz_comm_allgather_rows(demcz_ctx* c, int64_t phys_row0);
+int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);
+int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);
 int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n);
 int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);
 void demcz_comm_destroy_internal(demcz_ctx* c);

@@ -415,6 +415,7 @@ extern "C" void demcz_destroy(demcz_ctx* c)
                     c->d_scratch, c->d_stage};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : c->ev_xchg) cudaEventDestroy(ev);
     if (c->ev_run[0]) { cudaEventDestroy(c->ev_run[0]); cudaEventDestroy(c->ev_run[1]); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -472,9 +473,12 @@ extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
     if (cap < M0) cap = M0;
     if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
     if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
-    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->ZS * sizeof(float)));
+    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->ZS * sizeof(float) + 256));      // + 8 x 8-byte segment flags written by the peers
+    CU(c, cudaMemsetAsync(c->dZ + (size_t)cap * c->ZS, 0, 256, c->stream));
     c->zcap = cap;
     c->M = M0;
+    c->appends = 0;
+    c->vis_waited = 0;
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, (size_t)M0 * o.d * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(stage, Z, (size_t)M0 * o.d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -563,6 +567,66 @@ static int init_state_if_needed(demcz_ctx* c)
     return DEMCZ_OK;
 }
 
+// The rows a proposal may draw from, as (count, physical row of logical row 0).
+//  * overlap sync mode: the newest appended segment is not drawable yet (it is still being exchanged under this
+//    K-block's compute) — on every rank and for every world size, so results do not depend on the sharding;
+//  * ring buffer about to wrap: the N_global oldest rows, which this K-block's own append will overwrite while
+//    other threads may still be gathering, are excluded as well (keeps runs bit-reproducible).
+// Also makes the compute stream wait until the newest drawable segment has landed from every rank.
+int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart)
+{
+    const demcz_opts& o = c->o;
+    const int64_t pend = (o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends > 0) ? o.N_global : 0;
+    int64_t m, z0;
+    const bool more_appends = c->appends_run < (int64_t)o.Ngeneration / o.K;      // will this context append again?
+    if (more_appends && c->M + o.N_global > c->zcap) {       // the next append overwrites the oldest rows: keep off them
+        z0 = (c->M + o.N_global) % c->zcap;
+        m = c->zcap - o.N_global - pend;
+    } else if (c->M > c->zcap) {                             // wrapped ring, no further append
+        z0 = c->M % c->zcap;
+        m = c->zcap - pend;
+    } else {
+        z0 = 0;
+        m = c->M - pend;
+    }
+    if (m < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: fewer than 2 drawable archive rows (M=%lld, capacity=%lld)", (long long)c->M, (long long)c->zcap);
+    *Mdraw = (uint32_t)m;
+    *zstart = (uint32_t)z0;
+    if (o.world > 1 && o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends >= 2 && c->vis_waited < c->appends - 1) {
+        // segments 0 .. appends-2 become drawable: this rank's own exchange of them must be done (event) and, with the
+        // push transport, every peer's rows must have landed here (flag words)
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 2) & 1], 0));
+        int rc = demcz_comm_wait_segment(c, c->appends - 1);
+        if (rc != DEMCZ_OK) return rc;
+        c->vis_waited = c->appends - 1;
+    }
+    return DEMCZ_OK;
+}
+
+// After the kernel that wrote this rank's rows of the next segment has been launched: exchange, advance M.
+int demcz_archive_appended(demcz_ctx* c)
+{
+    const demcz_opts& o = c->o;
+    const int64_t row0 = c->M % c->zcap;
+    if (o.world > 1) {
+        if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
+            const int slot = (int)(c->appends & 1);
+            CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
+            CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
+            int rc = demcz_comm_exchange(c, row0, true);
+            if (rc != DEMCZ_OK) return rc;
+            CU(c, cudaEventRecord(c->ev_vis[slot], c->comm_stream));
+        } else {
+            int rc = demcz_comm_exchange(c, row0, false);
+            if (rc != DEMCZ_OK) return rc;
+        }
+    }
+    c->M += o.N_global;
+    c->appends += 1;
+    c->appends_run += 1;
+    return DEMCZ_OK;
+}
+
 static cudaEvent_t pool_event(demcz_ctx* c, size_t i)
 {
     while (c->ev_pool.size() <= i) {
@@ -644,6 +708,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     if (max_generations > 0 && g_begin + max_generations < g_end) g_end = g_begin + max_generations;
     const int every = o.autostop_every, nhalf = every / 2;
     size_t n_launch = 0;
+    c->xchg_used = 0;
     const unsigned long long lin_launch0 = demcz_linreg_launches(c);
     if (c->lik_kind == DEMCZ_LIK_LINREG) demcz_linreg_profile_ms(c, nullptr);      // drop brackets of earlier calls
     bool stopped = false;
@@ -676,9 +741,9 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.X = c->dX; a.logp = c->dlogp; a.N = o.N; a.ldx = c->ldx; a.d = o.d;
             a.chain_offset = (uint32_t)o.chain_offset;
             a.Z = c->dZ;
-            a.Mdraw = (uint32_t)std::min<int64_t>(c->M, c->zcap);
             a.zcap = (uint32_t)c->zcap;
-            a.zstart = c->M > c->zcap ? (uint32_t)(c->M % c->zcap) : 0u;
+            rc = demcz_archive_view(c, &a.Mdraw, &a.zstart);
+            if (rc != DEMCZ_OK) return rc;
             a.gen0 = o.gen_offset + g + 1;
             a.grel0 = g + 1;
             a.n_gens = n_gens;
@@ -705,7 +770,6 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.win_skip_gi = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : -1;
             if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift2, c->shift, sizeof a.shift2); }
 
-            if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             const bool full = o.Nblocks == 1 && a.blocks[0].mask == (o.d == 32 ? 0xFFFFFFFFu : ((1u << o.d) - 1u));
             CU(c, launch_step(c, a, acc, full));
@@ -716,11 +780,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
 
         // ---- archive append + exchange (src/demcz.jl:88-91; sync mode :129-137) -----------------
         if (append) {
-            if (o.world > 1) {
-                rc = demcz_comm_allgather_rows(c, (int64_t)(c->M % c->zcap));
-                if (rc != DEMCZ_OK) return rc;
-            }
-            c->M += o.N_global;
+            rc = demcz_archive_appended(c);
+            if (rc != DEMCZ_OK) return rc;
         }
         g = gb;
         c->g_done = g;
@@ -744,8 +805,14 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (c->rhat_max < o.autostop_Rhat) stopped = true;
         }
     }
+    if (o.world > 1 && o.sync_mode == DEMCZ_SYNC_OVERLAP) {                  // drain the exchange: the archive is complete when the call returns
+        if (c->appends > 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 1) & 1], 0));
+        rc = demcz_comm_wait_segment(c, c->appends);
+        if (rc != DEMCZ_OK) return rc;
+    }
     CU(c, cudaEventRecord(c->ev_run[1], c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
+    if (c->comm_stream) CU(c, cudaStreamSynchronize(c->comm_stream));
     if (stopped) c->stopped_by_rhat = true;
 
     if (info) {
@@ -774,6 +841,13 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             }
             if (c->lik_kind == DEMCZ_LIK_LINREG) tot = demcz_linreg_profile_ms(c, nullptr);
             info->step_kernel_ms = tot;
+            double xt = 0.0;
+            for (size_t i = 0; i + 1 < c->xchg_used; i += 2) {
+                float t = 0.f;
+                if (cudaEventElapsedTime(&t, c->ev_xchg[i], c->ev_xchg[i + 1]) == cudaSuccess) xt += t;
+            }
+            info->exchange_ms = xt;
+            info->exchanges = (int64_t)(c->xchg_used / 2);
         }
     }
     return DEMCZ_OK;

@@ -772,6 +772,8 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
     if (!s) return demcz_fail(c, DEMCZ_ERR_INVALID, "linreg likelihood not set");
     const demcz_opts& o = c->o;
     const int CT = s->Npad / 128;
+    uint32_t Mdraw = 0, zstart = 0;
+    { int rc = demcz_archive_view(c, &Mdraw, &zstart); if (rc != DEMCZ_OK) return rc; }
     for (int gi = 0; gi < n_gens; ++gi) {
         const int64_t grel = g + gi + 1;
         for (int b = 0; b < o.Nblocks; ++b) {
@@ -780,9 +782,7 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             a.X = c->dX; a.N = o.N; a.ldx = c->ldx; a.d = o.d; a.ppad = s->ppad;
             a.chain_offset = (uint32_t)o.chain_offset;
             a.Z = c->dZ; a.ZS = c->ZS;
-            a.Mdraw = (uint32_t)std::min<int64_t>(c->M, c->zcap);
-            a.zcap = (uint32_t)c->zcap;
-            a.zstart = c->M > c->zcap ? (uint32_t)(c->M % c->zcap) : 0u;
+            a.Mdraw = Mdraw; a.zcap = (uint32_t)c->zcap; a.zstart = zstart;
             a.gen = o.gen_offset + grel; a.grel = grel;
             a.keys = c->keys;
             a.block = b; a.nblocks = o.Nblocks;
@@ -794,7 +794,6 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
             a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
             a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
-            if (a.Mdraw < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: archive has fewer than 2 rows");
             linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true);
             CUL(c, cudaGetLastError());
 

@@ -14,7 +14,7 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard", "env_rank_world", "broadcast_unique_id", "make_sharded_sampler"]
+__all__ = ["shard", "env_rank_world", "broadcast_unique_id", "make_sharded_sampler", "open_peer_archives"]
 
 
 def shard(N_global: int, rank: int, world: int) -> Tuple[int, int]:
@@ -72,3 +72,21 @@ def make_sharded_sampler(logobj, d, *, N_global, rank=None, world=None, device=N
         uid = broadcast_unique_id(make_id, rank, device=torch.device("cuda", device))
         s.comm_init(uid)
     return s
+
+
+def open_peer_archives(s, rank=None, world=None, device=None, group=None):
+    """After `s.set_archive(...)` on every rank: all-gather the 128-byte peer records and open the peers' archive
+    replicas, so that appended rows are pushed straight into them over NVLink by the library's own kernel
+    (instead of ncclAllGather).  No-op for world == 1."""
+    import torch
+    import torch.distributed as dist
+    r, w, lr = env_rank_world()
+    rank = r if rank is None else rank
+    world = w if world is None else world
+    if world == 1:
+        return
+    dev = torch.device("cuda", lr if device is None else device) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.frombuffer(bytearray(s.peer_info()), dtype=torch.uint8).to(dev)
+    allinfo = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(world)]
+    dist.all_gather(allinfo, mine, group=group)
+    s.open_peers(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allinfo))

@@ -74,7 +74,7 @@ end
 struct CRunInfo
     generations_done::Int64; generations_total::Int64; stopped_by_rhat::Int32; rhat_valid::Int32
     rhat_max::Float64; final_gamma::Float64; M::Int64; proposals::Int64; accepted::Int64
-    step_launches::Int64; step_kernel_ms::Float64; device_ms::Float64
+    step_launches::Int64; step_kernel_ms::Float64; device_ms::Float64; exchange_ms::Float64; exchanges::Int64
 end
 
 function check(ctx, rc)
@@ -120,7 +120,7 @@ function run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale
             T = Float64[temperaturefun(ig, Ngeneration, T0, TN) for ig in 1:Ngeneration]
             check(ctx, ccall((:demcz_set_temperature_table, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx, T, length(T)))
         end
-        info = Ref(CRunInfo(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0))
+        info = Ref(CRunInfo(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0))
         check(ctx, ccall((:demcz_run, libdemcz[]), Cint, (Ptr{Cvoid}, Int64, Ref{CRunInfo}), ctx, 0, info))
         G = Int(info[].generations_total)
         chain = zeros(N, d, store_chain ? G : 0); log_obj = zeros(N, store_chain ? G : 0)

@@ -42,6 +42,9 @@ typedef enum {
 } demcz_status;
 
 enum { DEMCZ_INIT_LAST_N_OF_Z = 0, DEMCZ_INIT_REF_SERIAL_ZEROS = 1 };   /* SURVEY Q1 */
+/* STRICT: rows appended after generation g are drawable from generation g+1 (bit-identical to one GPU).
+ * OVERLAP: they become drawable one K-block later, on every rank and for every world size (also 1), so that the
+ * exchange of a segment runs under the next K-block's compute; results are still independent of the sharding. */
 enum { DEMCZ_SYNC_STRICT = 0, DEMCZ_SYNC_OVERLAP = 1 };
 
 /* Mirror of DEMCopt (src/DEMC.jl:24-39) + the keyword arguments of demcz_sample (src/demcz.jl:9)
@@ -95,6 +98,8 @@ typedef struct {
     int64_t step_launches;      /* step-kernel launches in this call */
     double step_kernel_ms;      /* sum of their device durations (profile=1), else 0 */
     double device_ms;           /* whole call on the context's stream, CUDA events */
+    double exchange_ms;         /* sum of the device durations of the archive exchanges of this call (profile=1) */
+    int64_t exchanges;
 } demcz_run_info;
 
 int demcz_version(void);
@@ -158,6 +163,12 @@ int demcz_get_trace(demcz_ctx* ctx, uint32_t* r1, uint32_t* r2, float* u, float*
  * demcz_comm_init before demcz_run. */
 int demcz_comm_unique_id(uint8_t id[128]);
 int demcz_comm_init(demcz_ctx* ctx, const uint8_t id[128]);
+/* Optional, after demcz_set_archive + demcz_comm_init on every rank: exchange the 128-byte peer records
+ * (all-gather on the host), then open them.  From then on a rank's appended rows are pushed by our own kernel
+ * straight into every peer's archive replica over NVLink (CUDA IPC / peer access) instead of ncclAllGather.
+ * infos: world x 128 bytes, in rank order. */
+int demcz_comm_peer_info(demcz_ctx* ctx, uint8_t info[128]);
+int demcz_comm_open_peers(demcz_ctx* ctx, const uint8_t* infos);
 
 #ifdef __cplusplus
 }

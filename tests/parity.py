@@ -34,7 +34,7 @@ def oracle_lik(logobj):
 
 def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, anneal=False, T0=3.0, TN=1e-3,
                              Ttable=None, gen_offset=0, init_mode="last_N_of_Z", X0=None, device=0, chunks=None,
-                             lp_rtol=LP_RTOL):
+                             lp_rtol=LP_RTOL, sync_mode="strict"):
     """Runs G generations on the GPU with trace + history and replays every proposal through the
     numpy oracle.  `chunks`: optional list of max_generations per demcz_run call (exercises resume
     inside one context).  Returns a dict of statistics; raises AssertionError on any mismatch."""
@@ -43,7 +43,7 @@ def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, a
     lik = oracle_lik(logobj)
     s = DEMC.Sampler(logobj, d, N=N, K=K, Ngeneration=G, blockindex=blocks, eps_scale=eps, γ=gamma, anneal=anneal,
                      T0=T0, TN=TN, seed=seed, gen_offset=gen_offset, store_chain=True, init_mode=init_mode,
-                     trace=True, device=device)
+                     trace=True, device=device, sync_mode=sync_mode)
     try:
         s.set_archive(Z0)
         if X0 is not None:
@@ -92,7 +92,10 @@ def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, a
     lp = lp_init.copy()
     nb = len(blocks)
     for g in range(1, G + 1):
-        M = M0 + N * ((g - 1) // K)                           # generation-synchronous archive
+        n_seg = (g - 1) // K                                  # generation-synchronous archive
+        if sync_mode == "overlap":                            # the newest segment is still in flight: not drawable yet
+            n_seg = max(n_seg - 1, 0)
+        M = M0 + N * n_seg
         T = Tt[g - 1] if anneal else None
         for ib, block in enumerate(blocks):
             o = orc.block_update(X, lp, Z, M, lik, block, ib, np.asarray(eps, dtype=np.float32).astype(np.float64),

@@ -16,12 +16,14 @@ from tests.parity import example_normpdf_target
 pytestmark = pytest.mark.gpu
 
 
-def _run_sharded(logobj_factory, d, Z0, N, world, **kw):
+def _run_sharded(logobj_factory, d, Z0, N, world, p2p=False, **kw):
     lib = _lib.load()
     buf = (C.c_uint8 * 128)()
     assert lib.demcz_comm_unique_id(buf) == 0
     uid = bytes(buf)
     out = [None] * world
+    infos = [None] * world
+    bar = threading.Barrier(world)
     err = []
 
     def work(r):
@@ -30,12 +32,18 @@ def _run_sharded(logobj_factory, d, Z0, N, world, **kw):
             s = DEMC.Sampler(logobj_factory(), d, N=n_loc, rank=r, world=world, N_global=N, chain_offset=off, device=r, **kw)
             s.set_archive(Z0)
             s.comm_init(uid)
+            if p2p:                                         # push kernel over peer-mapped archives instead of ncclAllGather
+                infos[r] = s.peer_info()
+                bar.wait(60)
+                s.open_peers(b"".join(infos))
+                bar.wait(60)
             info = s.run()
             X, lp = s.get_state()
             out[r] = (X, lp, s.get_archive(), info, s.get_rhat() if info["rhat_valid"] else None)
             s.close()
         except Exception as e:  # noqa: BLE001
             err.append(e)
+            bar.abort()
 
     th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
     for t in th:
@@ -47,19 +55,20 @@ def _run_sharded(logobj_factory, d, Z0, N, world, **kw):
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-def test_two_gpus_reproduce_one_gpu_bitwise():
+@pytest.mark.parametrize("sync_mode,p2p", [("strict", False), ("strict", True), ("overlap", False), ("overlap", True)])
+def test_two_gpus_reproduce_one_gpu_bitwise(sync_mode, p2p):
     d, N, K, G = 5, 256, 5, 40
     mu, S = example_normpdf_target(d)
     Z0 = np.random.default_rng(0).normal(size=(3 * N, d))
     kw = dict(K=K, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.38, seed=7,
-              store_chain=False, autostop=True, autostop_every=20, autostop_Rhat=0.0)
+              store_chain=False, autostop=True, autostop_every=20, autostop_Rhat=0.0, sync_mode=sync_mode)
     with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, device=0, **kw) as s:
         s.set_archive(Z0)
         info1 = s.run()
         X1, lp1 = s.get_state()
         Z1 = s.get_archive()
         rhat1 = s.get_rhat()
-    out = _run_sharded(lambda: DEMC.MvNormalLogpdf(mu, S), d, Z0, N, 2, **kw)
+    out = _run_sharded(lambda: DEMC.MvNormalLogpdf(mu, S), d, Z0, N, 2, p2p=p2p, **kw)
     X2 = np.concatenate([o[0] for o in out])
     lp2 = np.concatenate([o[1] for o in out])
     np.testing.assert_array_equal(X2, X1)

@@ -85,6 +85,14 @@ def test_init_modes_and_gen_offset_and_chunked_run():
     check_run_against_oracle(lo, _z0(60, d), X0=X0, **kw)                               # prevrun-style state
 
 
+def test_overlap_sync_mode_visibility_stepwise():
+    # DEMCZ_SYNC_OVERLAP: rows appended after K-block j become drawable from K-block j+2 (also on one GPU)
+    d, N = 5, 64
+    mu, S = example_normpdf_target(d)
+    check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(100, d), N=N, K=4, G=30, blocks=[list(range(d))],
+                             eps=1e-5 * np.ones(d), gamma=2.38, seed=3, sync_mode="overlap", chunks=[5, 9])
+
+
 def test_prevrun_continuation_is_bit_identical():
     # mc, Z = demcz_sample(...); mc, Z = demcz_sample(..., Z; prevrun=mc)   (test/example_normpdf.jl:30-32)
     d, N, K = 5, 20, 10
