@@ -11,9 +11,9 @@ Importing the package does not load CUDA; the first sampler call loads libdemcz_
 loudly if it (or a GPU) is missing — there is no CPU fallback.
 """
 from .api import (DEMCopt, MC, LinRegLoglik, MvNormalLogpdf, QuadraticLogobj, Sampler, demcopt, demcz_anneal,
-                  demcz_sample, tempbaseline)
+                  demcz_anneal_par, demcz_sample, demcz_sample_par, tempbaseline)
 from .utils import Rhat_gelman, convergence_check, flatten_chain, mean_cov_chain
 from . import _lib
 
 __all__ = ["DEMCopt", "MC", "LinRegLoglik", "MvNormalLogpdf", "QuadraticLogobj", "Sampler", "demcopt", "demcz_anneal",
-           "demcz_sample", "tempbaseline", "Rhat_gelman", "convergence_check", "flatten_chain", "mean_cov_chain"]
+           "demcz_sample", "demcz_sample_par", "demcz_anneal_par", "tempbaseline", "Rhat_gelman", "convergence_check", "flatten_chain", "mean_cov_chain"]

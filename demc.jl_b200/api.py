@@ -27,7 +27,7 @@ import numpy as np
 from . import _lib
 
 __all__ = ["DEMCopt", "demcopt", "MC", "MvNormalLogpdf", "QuadraticLogobj", "LinRegLoglik", "demcz_sample",
-           "demcz_anneal", "tempbaseline", "Sampler"]
+           "demcz_anneal", "demcz_sample_par", "demcz_anneal_par", "tempbaseline", "Sampler"]
 
 
 # ------------------------------------------------------------------------------------------------
@@ -436,3 +436,38 @@ def demcz_anneal(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=Non
                 adaptγ=dict(_ADAPT_DEFAULT) if adaptγ is None else adaptγ, seed=seed, device=device,
                 store_chain=store_chain, init_mode=init_mode, archive_capacity=archive_capacity, trace=trace,
                 profile=profile, **kw)
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference's parallel entry points (src/demcz.jl:101-165, src/demcz_anneal.jl:82-140)
+# ------------------------------------------------------------------------------------------------
+def demcz_sample_par(logobj, Zmat, *args, sync_every=1000, prevrun=None, workerpool=None, autostop=None, autostop_Rhat=None,
+                     verbose=None, **kw):
+    """demcz_sample_par(logobj, Zmat, opts | N, K, ...; sync_every, prevrun, autostop, autostop_Rhat, workerpool).
+
+    In the reference one Distributed.jl worker runs each chain for `sync_every` generations between barriers and the
+    master checks R-hat on every sync block (src/demcz.jl:129-155).  Here every chain is a GPU thread and the barrier is
+    the kernel boundary, so the entry point maps onto the same generation loop with `autostop_every = sync_every`;
+    `workerpool` is accepted and ignored.  Positional defaults follow src/demcz.jl:106 (autostop=:Rhat, Rhat < 1.1).
+    For several GPUs use demc_jl_b200.dist.make_sharded_sampler under torchrun."""
+    if len(args) == 1 and isinstance(args[0], DEMCopt):
+        o = args[0]
+        kw2 = dict(autostop=o.autostop, autostop_Rhat=o.autostop_Rhat, verbose=o.verbose)
+    else:
+        kw2 = dict(autostop="Rhat", autostop_Rhat=1.1, verbose=True)
+    for name, val in (("autostop", autostop), ("autostop_Rhat", autostop_Rhat), ("verbose", verbose)):
+        if val is not None:
+            kw2[name] = val
+    return demcz_sample(logobj, Zmat, *args, prevrun=prevrun, autostop_every=int(sync_every), **kw2, **kw)
+
+
+def demcz_anneal_par(logobj, Zmat, *args, sync_every=1000, prevrun=None, temperaturefun: Callable = tempbaseline, T0=None,
+                     TN=None, adaptγ=None, verbose=None, **kw):
+    """demcz_anneal_par (src/demcz_anneal.jl:82-140): γ is adapted once per sync block there, i.e. adapt_every = sync_every;
+    the positional form defaults to TN = 1e-3 (src/demcz_anneal.jl:86), unlike the serial one."""
+    ad = dict(_ADAPT_DEFAULT) if adaptγ is None else dict(adaptγ)
+    ad["adapt_every"] = int(sync_every)
+    if not (len(args) == 1 and isinstance(args[0], DEMCopt)) and TN is None:
+        TN = 1e-3
+    return demcz_anneal(logobj, Zmat, *args, prevrun=prevrun, temperaturefun=temperaturefun, T0=T0, TN=TN, adaptγ=ad,
+                        verbose=verbose, **kw)

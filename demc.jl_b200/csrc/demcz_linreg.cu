@@ -54,7 +54,7 @@ struct demcz_linreg_state {
     uint32_t* wacc = nullptr;                      // [ldx] accept word of the pending proposal
     int tile_n = 0, tiles = 0, R = 0, tiles_per_chunk = 0;
     int terms = 3;                                 // 3xTF32 (FP32-equivalent) or 1 (plain TF32; measurement only)
-    CUtensorMap tmXhi, tmXlo, tmDhi, tmDlo;
+    CUtensorMap tmXhi, tmXlo;
     int sms = 148;
     unsigned long long ssr_launches = 0;
     std::vector<cudaEvent_t> ev;                   // profile=1: brackets of the SSR kernel launches of the last run
@@ -329,47 +329,47 @@ __global__ void linreg_finish_eval_kernel(const double* __restrict__ partial, co
 // ------------------------------------------------------------------------------------------------
 // the tensor-core kernel:  partial[rc][chain] = sum over the rows of chunk rc of (x_row . d_chain)^2
 // ------------------------------------------------------------------------------------------------
-constexpr int kSsrThreads = 192;      // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2-5: epilogue
+constexpr int kEpiWarps = 8;          // two epilogue warps per TMEM lane quarter, each owning half of the tile's columns
+constexpr int kSsrThreads = 64 + 32 * kEpiWarps;   // warp 0: TMA producer, warp 1: MMA issuer + TMEM owner, warps 2..: epilogue
 
 template <int KB, int TILE_N, int STAGES>
 struct SsrSmem {
-    static constexpr int A_BYTES = KB * 128 * 128;                 // one of d_hi / d_lo: KB k-blocks of [128 chains][128 B]
     static constexpr int B_BYTES = KB * TILE_N * 128;              // one of X_hi / X_lo for one row tile
     static constexpr int STAGE_BYTES = 2 * B_BYTES;
-    static constexpr int BAR_OFF = 2 * A_BYTES + STAGES * STAGE_BYTES;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;             // barriers + tmem holder + 1024-byte alignment slack
 };
 
+// TMEM columns: [0, 2 TILE_N) two accumulator stages | d_hi (KB*32 columns) | d_lo (KB*32 columns)
 template <int KB, int TILE_N, int STAGES, int TERMS>
 __global__ void __launch_bounds__(kSsrThreads, 1)
 linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_constant__ CUtensorMap tmXlo,
-                  const __grid_constant__ CUtensorMap tmDhi, const __grid_constant__ CUtensorMap tmDlo, int ksteps, int tiles,
+                  const float* __restrict__ Dhi, const float* __restrict__ Dlo, int ppad, int ksteps, int tiles,
                   int tiles_per_chunk, int CT, int units, int npad, double* __restrict__ partial)
 {
     using L = SsrSmem<KB, TILE_N, STAGES>;
     constexpr int ACC = 2;                                         // TMEM accumulator stages
-    constexpr uint32_t TMEM_COLS = ACC * TILE_N;                   // 512 or 256 (power of two)
+    constexpr uint32_t A_COL = ACC * TILE_N;                       // first column of the chain tile
+    constexpr uint32_t TMEM_COLS = 512;
+    static_assert(A_COL + 2 * KB * 32 <= TMEM_COLS, "TMEM budget");
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* sA_hi = smem;
-    uint8_t* sA_lo = smem + L::A_BYTES;
-    uint8_t* sB = smem + 2 * L::A_BYTES;
+    uint8_t* sB = smem;
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
     uint64_t* full = bars;                 // [STAGES]  TMA -> MMA
     uint64_t* empty = bars + STAGES;       // [STAGES]  MMA -> TMA
-    uint64_t* a_full = bars + 2 * STAGES;  // chain tile landed
-    uint64_t* a_empty = a_full + 1;        // chain tile no longer read
-    uint64_t* tfull = a_empty + 1;         // [ACC] MMA -> epilogue
+    uint64_t* a_full = bars + 2 * STAGES;  // chain tile stored in TMEM
+    uint64_t* tfull = a_full + 1;          // [ACC] MMA -> epilogue
     uint64_t* tempty = tfull + ACC;        // [ACC] epilogue -> MMA
     uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + ACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     if (warp == 0 && lane == 0) {
-        tc::tma_prefetch_desc(&tmXhi); tc::tma_prefetch_desc(&tmXlo); tc::tma_prefetch_desc(&tmDhi); tc::tma_prefetch_desc(&tmDlo);
+        tc::tma_prefetch_desc(&tmXhi); tc::tma_prefetch_desc(&tmXlo);
         for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        tc::mbar_init(a_full, 1); tc::mbar_init(a_empty, 1);
-        for (int s = 0; s < ACC; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], 4); }
+        tc::mbar_init(a_full, kEpiWarps);
+        for (int s = 0; s < ACC; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], kEpiWarps); }
         tc::fence_barrier_init();
     }
     if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
@@ -379,18 +379,11 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
     const uint32_t tmem_base = *tmem_holder;
 
     if (warp == 0) {
-        // ===================== TMA producer =====================
+        // ===================== TMA producer: streams the X tiles of all this CTA's units =====================
         if (lane == 0) {
-            int stage = 0; uint32_t ph = 0, aph = 0;
+            int stage = 0; uint32_t ph = 0;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int rc = u / CT, ct = u - rc * CT;
-                tc::mbar_wait(a_empty, aph ^ 1);
-                tc::mbar_arrive_expect_tx(a_full, 2 * L::A_BYTES);
-                for (int kb = 0; kb < KB; ++kb) {
-                    tc::tma_load_2d(sA_hi + kb * 128 * 128, &tmDhi, kb * 32, ct * 128, a_full);
-                    tc::tma_load_2d(sA_lo + kb * 128 * 128, &tmDlo, kb * 32, ct * 128, a_full);
-                }
-                aph ^= 1;
+                const int rc = u / CT;
                 const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
                 for (int t = t0; t < t1; ++t) {
                     tc::mbar_wait(&empty[stage], ph ^ 1);
@@ -410,11 +403,12 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
         if (lane == 0) {
             constexpr uint32_t idesc = tc::make_idesc_tf32(128, TILE_N);
             int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
-            const uint64_t a_hi0 = tc::make_sw128_kmajor_desc(sA_hi), a_lo0 = tc::make_sw128_kmajor_desc(sA_lo);
+            const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + KB * 32;
             for (int u = blockIdx.x; u < units; u += gridDim.x) {
                 const int rc = u / CT;
-                tc::mbar_wait(a_full, aph);
+                tc::mbar_wait(a_full, aph);                    // the epilogue warps stored this unit's chain tile
                 aph ^= 1;
+                tc::tc_fence_after();
                 const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
                 for (int t = t0; t < t1; ++t) {
                     tc::mbar_wait(&tempty[as], tph ^ 1);
@@ -424,57 +418,73 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
                     const uint64_t b_hi0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
                     const uint64_t b_lo0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES + L::B_BYTES);
                     uint32_t accum = 0;
-                    // a k-step is 8 TF32 = 32 bytes inside the 128-byte swizzle row (descriptor start address + 2),
-                    // a k-block is the next [rows][128 B] panel.  Small cross terms first, hi*hi last.
+                    // a k-step is 8 TF32: 8 TMEM columns of the chain tile, 32 bytes inside the 128-byte swizzle row of X
+                    // (descriptor start address + 2); a k-block is the next [rows][128 B] panel.  Cross terms first.
                     if (TERMS == 3) {
                         for (int ks = 0; ks < ksteps; ++ks) {
-                            const uint64_t ao = (uint64_t)(((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4);
                             const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
-                            tc::mma_tf32_ss(d_tmem, a_lo0 + ao, b_hi0 + bo, idesc, accum); accum = 1;
-                            tc::mma_tf32_ss(d_tmem, a_hi0 + ao, b_lo0 + bo, idesc, accum);
+                            tc::mma_tf32_ts(d_tmem, a_lo + ks * 8, b_hi0 + bo, idesc, accum); accum = 1;
+                            tc::mma_tf32_ts(d_tmem, a_hi + ks * 8, b_lo0 + bo, idesc, accum);
                         }
                     }
                     for (int ks = 0; ks < ksteps; ++ks) {
-                        const uint64_t ao = (uint64_t)(((ks >> 2) * 128 * 128 + (ks & 3) * 32) >> 4);
                         const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
-                        tc::mma_tf32_ss(d_tmem, a_hi0 + ao, b_hi0 + bo, idesc, accum); accum = 1;
+                        tc::mma_tf32_ts(d_tmem, a_hi + ks * 8, b_hi0 + bo, idesc, accum); accum = 1;
                     }
                     tc::mma_commit(&empty[stage]);             // X tile consumed -> producer may refill
                     tc::mma_commit(&tfull[as]);                // accumulator ready -> epilogue
                     if (++stage == STAGES) { stage = 0; ph ^= 1; }
                     if (++as == ACC) { as = 0; tph ^= 1; }
                 }
-                tc::mma_commit(a_empty);                       // chain tile no longer read
             }
         }
     } else {
-        // ===================== epilogue: square-and-sum =====================
+        // ===================== epilogue warps: chain tile -> TMEM, then square-and-sum =====================
+        constexpr int HALVES = kEpiWarps / 4;                  // column ranges per lane quarter
+        constexpr int COLS = TILE_N / HALVES;
+        static_assert(COLS % 32 == 0, "epilogue column split");
         const int quarter = warp & 3;                          // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;                      // which column range of the tile
         int as = 0; uint32_t tph = 0;
         for (int u = blockIdx.x; u < units; u += gridDim.x) {
             const int rc = u / CT, ct = u - rc * CT;
+            // All MMAs of the previous unit are complete (its last accumulator was consumed below), so the chain tile
+            // in TMEM can be replaced: lane = chain, columns = the KB*32 coefficients, hi by one warp of the quarter,
+            // lo by the other.
+            {
+                const float* src = (half == 0 ? Dhi : Dlo) + (size_t)(ct * 128 + quarter * 32 + lane) * ppad;
+                const uint32_t acol = A_COL + (half == 0 ? 0 : KB * 32);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) {
+                    float v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const float4 t4 = *reinterpret_cast<const float4*>(src + kb * 32 + j);
+                        v[j] = t4.x; v[j + 1] = t4.y; v[j + 2] = t4.z; v[j + 3] = t4.w;
+                    }
+                    tc::tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + acol + kb * 32, v);
+                }
+                tc::tmem_st_wait();
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(a_full);
+            }
             const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
             double accd = 0.0;
             for (int t = t0; t < t1; ++t) {
                 tc::mbar_wait(&tfull[as], tph);
                 tc::tc_fence_after();
-                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TILE_N);
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TILE_N + half * COLS);
                 float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll 1
-                for (int c = 0; c < TILE_N; c += 64) {
-                    float v[32], w[32];
+#pragma unroll
+                for (int c = 0; c < COLS; c += 32) {
+                    float v[32];
                     tc::tmem_ld32(taddr + c, v);
-                    tc::tmem_ld32(taddr + c + 32, w);
                     tc::tmem_ld_wait();
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
                         s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
                         s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
-                    }
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s0 = fmaf(w[j], w[j], s0); s1 = fmaf(w[j + 1], w[j + 1], s1);
-                        s2 = fmaf(w[j + 2], w[j + 2], s2); s3 = fmaf(w[j + 3], w[j + 3], s3);
                     }
                 }
                 tc::tc_fence_before();
@@ -483,7 +493,7 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
                 accd += (double)((s0 + s1) + (s2 + s3));
                 if (++as == ACC) { as = 0; tph ^= 1; }
             }
-            partial[(size_t)rc * npad + ct * 128 + quarter * 32 + lane] = accd;
+            partial[(size_t)(rc * HALVES + half) * npad + ct * 128 + quarter * 32 + lane] = accd;
         }
     }
 
@@ -528,8 +538,7 @@ int make_map(demcz_ctx* c, CUtensorMap* m, const float* base, uint64_t rows, int
 }
 
 template <int KB, int TILE_N, int STAGES, int TERMS>
-cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& dhi, const CUtensorMap& dlo, int CT, int npad,
-                         double* partial)
+cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial)
 {
     auto kern = linreg_ssr_kernel<KB, TILE_N, STAGES, TERMS>;
     constexpr int smem = SsrSmem<KB, TILE_N, STAGES>::TOTAL;
@@ -541,20 +550,21 @@ cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap&
     }
     const int units = CT * s->R;
     const int grid = std::min(units, s->sms);
-    kern<<<grid, kSsrThreads, smem, c->stream>>>(s->tmXhi, s->tmXlo, dhi, dlo, s->ksteps, s->tiles, s->tiles_per_chunk, CT, units,
-                                                 npad, partial);
+    kern<<<grid, kSsrThreads, smem, c->stream>>>(s->tmXhi, s->tmXlo, dhi, dlo, s->ppad, s->ksteps, s->tiles, s->tiles_per_chunk, CT,
+                                                 units, npad, partial);
     return cudaGetLastError();
 }
 
-cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& dhi, const CUtensorMap& dlo, int CT, int npad,
-                       double* partial)
+constexpr int kTileN32 = 192, kTileN64 = 128;     // data rows per MMA (N) for p <= 32 / p <= 64: 2 N + chain-tile columns <= 512 TMEM columns
+
+cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial)
 {
     if (s->ppad == 32) {
-        if (s->terms == 3) return launch_ssr_t<1, 256, 3, 3>(c, s, dhi, dlo, CT, npad, partial);
-        return launch_ssr_t<1, 256, 3, 1>(c, s, dhi, dlo, CT, npad, partial);
+        if (s->terms == 3) return launch_ssr_t<1, kTileN32, 4, 3>(c, s, dhi, dlo, CT, npad, partial);
+        return launch_ssr_t<1, kTileN32, 4, 1>(c, s, dhi, dlo, CT, npad, partial);
     }
-    if (s->terms == 3) return launch_ssr_t<2, 128, 2, 3>(c, s, dhi, dlo, CT, npad, partial);
-    return launch_ssr_t<2, 128, 2, 1>(c, s, dhi, dlo, CT, npad, partial);
+    if (s->terms == 3) return launch_ssr_t<2, kTileN64, 3, 3>(c, s, dhi, dlo, CT, npad, partial);
+    return launch_ssr_t<2, kTileN64, 3, 1>(c, s, dhi, dlo, CT, npad, partial);
 }
 
 inline int grid1(long long n, int t = 256) { return (int)((n + t - 1) / t); }
@@ -591,7 +601,7 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     c->linreg = s;
     const demcz_opts& o = c->o;
     s->n = n; s->p = p; s->ppad = p <= 32 ? 32 : 64; s->ksteps = (p + 7) / 8;
-    s->tile_n = s->ppad == 32 ? 256 : 128;
+    s->tile_n = s->ppad == 32 ? kTileN32 : kTileN64;
     s->tiles = (int)((n + s->tile_n - 1) / s->tile_n);
     s->R = std::max(1, std::min(37, s->tiles / 8));                 // row chunks: 37 | 148 keeps (chain tiles x chunks) balanced over the SMs
     s->tiles_per_chunk = (s->tiles + s->R - 1) / s->R;
@@ -610,7 +620,7 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     CUL(c, cudaMalloc((void**)&s->Dlo, (size_t)s->Npad * s->ppad * sizeof(float)));
     CUL(c, cudaMalloc((void**)&s->Xprop, (size_t)c->ldx * o.d * sizeof(float)));
     CUL(c, cudaMalloc((void**)&s->lin, (size_t)s->Npad * sizeof(double)));
-    CUL(c, cudaMalloc((void**)&s->partial, (size_t)s->R * s->Npad * sizeof(double)));
+    CUL(c, cudaMalloc((void**)&s->partial, (size_t)s->R * (kEpiWarps / 4) * s->Npad * sizeof(double)));
     CUL(c, cudaMalloc((void**)&s->lp64, (size_t)c->ldx * 2 * sizeof(double)));      // [lp | lp at generation start]
     CUL(c, cudaMalloc((void**)&s->wacc, (size_t)c->ldx * sizeof(uint32_t)));
     CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
@@ -695,8 +705,6 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
 
     int rc = make_map(c, &s->tmXhi, s->Xhi, (uint64_t)n, s->ppad, s->tile_n);
     if (rc == DEMCZ_OK) rc = make_map(c, &s->tmXlo, s->Xlo, (uint64_t)n, s->ppad, s->tile_n);
-    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmDhi, s->Dhi, (uint64_t)s->Npad, s->ppad, 128);
-    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmDlo, s->Dlo, (uint64_t)s->Npad, s->ppad, 128);
     if (rc != DEMCZ_OK) return rc;
     c->lik_kind = DEMCZ_LIK_LINREG;
     c->state_lp_valid = false;
@@ -713,18 +721,14 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
     const bool own_state = (out_dev == nullptr);           // the context's own chains -> lp64
     const int npad = (n + 127) / 128 * 128;
     float *dhi = s->Dhi, *dlo = s->Dlo; double *lin = s->lin, *partial = s->partial;
-    CUtensorMap mh = s->tmDhi, ml = s->tmDlo;
     void* tmp = nullptr;
     if (npad > s->Npad) {                                   // evaluation of more points than chains: temporaries
         const size_t fb = (size_t)npad * s->ppad * sizeof(float);
-        const size_t total = 2 * fb + (size_t)npad * sizeof(double) * (1 + s->R);
+        const size_t total = 2 * fb + (size_t)npad * sizeof(double) * (1 + s->R * (kEpiWarps / 4));
         CUL(c, cudaMalloc(&tmp, total));
         CUL(c, cudaMemsetAsync(tmp, 0, total, c->stream));
         dhi = (float*)tmp; dlo = (float*)((char*)tmp + fb);
         lin = (double*)((char*)tmp + 2 * fb); partial = lin + npad;
-        int rc = make_map(c, &mh, dhi, (uint64_t)npad, s->ppad, 128);
-        if (rc == DEMCZ_OK) rc = make_map(c, &ml, dlo, (uint64_t)npad, s->ppad, 128);
-        if (rc != DEMCZ_OK) { cudaFree(tmp); return rc; }
     }
     LinArgs a;
     memset(&a, 0, sizeof a);
@@ -733,9 +737,9 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
     linreg_prepare_kernel<<<grid1(n, 128), 128, 0, c->stream>>>(a, false);
     cudaError_t e = cudaGetLastError();
     const int use_npad = npad > s->Npad ? npad : s->Npad;
-    if (e == cudaSuccess) e = launch_ssr(c, s, mh, ml, npad / 128, use_npad, partial);
+    if (e == cudaSuccess) e = launch_ssr(c, s, dhi, dlo, npad / 128, use_npad, partial);
     if (e == cudaSuccess) {
-        linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R, s->ssr0, own_state ? s->lp64 : out_dev);
+        linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R * (kEpiWarps / 4), s->ssr0, own_state ? s->lp64 : out_dev);
         e = cudaGetLastError();
     }
     s->ssr_launches++;
@@ -801,14 +805,14 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
                 while (s->ev.size() < s->ev_used + 2) { cudaEvent_t ev; CUL(c, cudaEventCreate(&ev)); s->ev.push_back(ev); }
                 CUL(c, cudaEventRecord(s->ev[s->ev_used], c->stream));
             }
-            CUL(c, launch_ssr(c, s, s->tmDhi, s->tmDlo, CT, s->Npad, s->partial));
+            CUL(c, launch_ssr(c, s, s->Dhi, s->Dlo, CT, s->Npad, s->partial));
             if (o.profile) { CUL(c, cudaEventRecord(s->ev[s->ev_used + 1], c->stream)); s->ev_used += 2; }
             s->ssr_launches++;
 
             AccArgs q;
             memset(&q, 0, sizeof q);
             q.X = c->dX; q.Xprop = s->Xprop; q.lp = s->lp64; q.wacc = s->wacc;
-            q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R;
+            q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R * (kEpiWarps / 4);
             q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0;
             q.tempered = o.anneal ? 1 : 0;
             q.T = o.anneal ? c->hT[(size_t)grel - 1] : 1.f;

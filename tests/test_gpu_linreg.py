@@ -121,3 +121,17 @@ def test_example_linreg_posterior_matches_ols():
     accept_ratio, Rhat = DEMC.convergence_check(keep, mc.log_obj[:, -W:], verbose=False)
     assert np.all(Rhat < 1.1)                             # the reference's autostop threshold in this example
     assert 0.05 < accept_ratio.mean() < 0.5
+
+
+def test_linreg_streaming_rhat_and_par_entry_point():
+    # autostop R-hat from the streaming accumulators of the linreg accept kernel vs Rhat_gelman (src/utils.jl:2-20) on the
+    # stored window; driven through the reference's parallel entry point demcz_sample_par (sync_every = R-hat window)
+    X, y, _ = example_linreg_data(1500, 7)
+    d, N, every = 8, 96, 60
+    bols = np.linalg.solve(X.T @ X, X.T @ y)
+    Z0 = bols + 0.05 * np.random.default_rng(8).normal(size=(4 * N, d))
+    mc, Z = DEMC.demcz_sample_par(DEMC.LinRegLoglik(X, y), Z0, N, 10, 2 * every, 1, [list(range(d))], 1e-5 * np.ones(d), 2.0,
+                                  sync_every=every, autostop="Rhat", autostop_Rhat=0.0, verbose=False)
+    assert mc.chain.shape == (N, d, 2 * every) and mc.info["rhat_valid"]
+    ref = orc.rhat_gelman(mc.chain[:, :, every:])
+    np.testing.assert_allclose(mc.info["rhat"], ref, rtol=5e-4)

@@ -57,6 +57,49 @@ float run_variant(StepArgs a, const std::vector<float>& Wfull, const std::vector
     return ms / reps;
 }
 
+// Upper bound probe: nothing but the random row fetch (C 16-byte pieces of `U` independent random rows per thread in
+// flight), no Philox, no staging, no likelihood.  rows/s here is what the HBM system delivers for this access pattern.
+template <int C, int U>
+__global__ void gather_probe_kernel(const float* __restrict__ Z, uint32_t M, int ZS, int rounds, float* __restrict__ out)
+{
+    uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
+    float acc = 0.f;
+    for (int r = 0; r < rounds; ++r) {
+        float4 v[U][C];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            h = h * 1664525u + 1013904223u;
+            const uint32_t row = __umulhi(h ^ (h >> 15), M);
+            const float4* p = reinterpret_cast<const float4*>(Z + (size_t)row * ZS);
+#pragma unroll
+            for (int c = 0; c < C; ++c) v[u][c] = __ldcg(p + c);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+            for (int c = 0; c < C; ++c) acc += v[u][c].x + v[u][c].w;
+    }
+    if (acc == 123.456f) out[0] = acc;
+}
+
+template <int C, int U>
+void run_probe(const float* Z, uint32_t M, int ZS, float* out, const char* what)
+{
+    const int threads = 256, blocks = 148 * 8, rounds = 16;
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));
+    gather_probe_kernel<C, U><<<blocks, threads>>>(Z, M, ZS, rounds, out);
+    CK(cudaDeviceSynchronize());
+    CK(cudaEventRecord(e0));
+    for (int i = 0; i < 5; ++i) gather_probe_kernel<C, U><<<blocks, threads>>>(Z, M, ZS, rounds, out);
+    CK(cudaEventRecord(e1));
+    CK(cudaDeviceSynchronize());
+    float ms = 0; CK(cudaEventElapsedTime(&ms, e0, e1));
+    const double rows = 5.0 * blocks * threads * rounds * U;
+    printf("gather probe %-28s: %7.2f G rows/s  = %6.0f GB/s of 128-B line fills, %6.0f GB/s of row payload (%d B)\n", what,
+           rows / (ms * 1e-3) / 1e9, rows * 128 / (ms * 1e-3) / 1e9, rows * C * 16 / (ms * 1e-3) / 1e9, C * 16);
+}
+
 int main(int argc, char** argv)
 {
     const int N = 131072, d = 20, ldx = N;
@@ -91,6 +134,10 @@ int main(int argc, char** argv)
     for (int k = 0; k < d; ++k) (&a.shift2[0].x)[k] = mu[k];
 
     auto reset = [&]() { CK(cudaMemcpy(X, hx.data(), hx.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(logp, hl.data(), N * 4, cudaMemcpyHostToDevice)); };
+    run_probe<5, 4>(Z, (uint32_t)M0, ZS, S1, "80-B rows, 4 rows in flight");
+    run_probe<5, 8>(Z, (uint32_t)M0, ZS, S1, "80-B rows, 8 rows in flight");
+    run_probe<8, 8>(Z, (uint32_t)M0, ZS, S1, "128-B rows, 8 rows in flight");
+    run_probe<1, 16>(Z, (uint32_t)M0, ZS, S1, "16-B piece, 16 in flight");
     double cs;
     const int reps = 20;
 #define RUN(MINB, OPT) reset(); run_variant<MINB, OPT>(a, W, mu, reps, &cs);
