@@ -230,3 +230,29 @@ def test_moments_api():
     X32 = X0.astype(np.float32).astype(np.float64)
     np.testing.assert_allclose(m, X32.mean(axis=0), rtol=1e-10, atol=1e-12)
     np.testing.assert_allclose(c, np.cov(X32.T, bias=True), rtol=1e-8, atol=1e-12)
+
+
+@pytest.mark.parametrize("d,N,K,G,M0", [
+    (3, 1, 2, 9, 2),        # a single chain, the smallest legal archive (2 rows: r1 != r2 is forced)
+    (2, 5, 50, 12, 7),      # K > G: the archive never grows
+    (4, 33, 1, 6, 40),      # append after every generation, ragged N
+])
+def test_edge_sizes_stepwise(d, N, K, G, M0):
+    mu, S = example_normpdf_target(d, seed=d + N)
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(M0, d, seed=M0, scale=0.2), N=N, K=K, G=G,
+                                  blocks=[list(range(d))], eps=1e-4 * np.ones(d), gamma=2.38, seed=99,
+                                  X0=(mu + 0.05 * np.random.default_rng(N).normal(size=(N, d))) if M0 < N else None)
+    assert st["proposals"] == N * G
+
+
+def test_zero_generations_and_state_only():
+    d, N = 3, 8
+    mu, S = example_normpdf_target(d)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=10, Ngeneration=0, blockindex=[list(range(d))],
+                      eps_scale=np.ones(d), γ=2.38) as s:
+        s.set_archive(_z0(20, d))
+        info = s.run()
+        assert info["generations_total"] == 0 and info["M"] == 20
+        X, lp = s.get_state()
+        np.testing.assert_array_equal(X, _z0(20, d)[-N:].astype(np.float32).astype(np.float64))
+        assert s.get_archive().shape == (20, d)
