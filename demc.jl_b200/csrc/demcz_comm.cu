@@ -280,7 +280,7 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
         PeerPtrs pp;
         int np = 0;
         for (int r = 0; r < c->o.world; ++r) if (r != c->o.rank) pp.p[np++] = c->peerZ[r];
-        const int C = c->LD / 4;
+        const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
         const long long total = (long long)c->o.N * C;
         const int grid = (int)std::min<long long>(32, (total + 255) / 256);      // measured: 16..128 CTAs move the same bytes/s (link-bound)
         const unsigned long long seq = (unsigned long long)c->appends + 1;       // this is segment number `appends`
