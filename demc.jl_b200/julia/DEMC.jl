@@ -168,4 +168,23 @@ function demcz_anneal(logobj, Zmat, N=4, K=10, Ngeneration=5000, Nblocks=1, bloc
             autostop_Rhat=1.01, autostop_every=1000, T0=Float64(T0), TN=Float64(TN), temperaturefun=temperaturefun, adaptγ=adaptγ)
 end
 
+# ---- the parallel entry points (src/demcz.jl:101-165, src/demcz_anneal.jl:82-140): every chain is a GPU thread, the
+# sync block is the R-hat / γ-adaptation window; `workerpool` is accepted and ignored ------------------------------
+function demcz_sample_par(logobj, Zmat, opts::DEMCopt; sync_every=1000, prevrun=nothing, workerpool=nothing)
+    demcz_sample(logobj, Zmat, opts.N, opts.K, opts.Ngeneration, opts.Nblocks, opts.blockindex, opts.eps_scale, opts.γ;
+                 prevrun=prevrun, verbose=opts.verbose, autostop=opts.autostop, autostop_Rhat=opts.autostop_Rhat, autostop_every=sync_every)
+end
+
+function demcz_sample_par(logobj, Zmat, N=4, K=10, Ngeneration=5000, Nblocks=1, blockindex=[1:size(Zmat, 2)], eps_scale=1e-4 * ones(size(Zmat, 2)), γ=2.38;
+                          sync_every=1000, prevrun=nothing, autostop=:Rhat, autostop_Rhat=1.1, verbose=true, workerpool=nothing)
+    demcz_sample(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale, γ; prevrun=prevrun, verbose=verbose,
+                 autostop=autostop, autostop_Rhat=autostop_Rhat, autostop_every=sync_every)
+end
+
+function demcz_anneal_par(logobj, Zmat, opts::DEMCopt; prevrun=nothing, temperaturefun=tempbaseline, sync_every=1000,
+                          adaptγ=Dict("adapt" => true, "minγ" => 0.1, "maxγ" => 4.0, "adapt_every" => 500))
+    ad = copy(adaptγ); ad["adapt_every"] = sync_every
+    demcz_anneal(logobj, Zmat, opts; prevrun=prevrun, temperaturefun=temperaturefun, adaptγ=ad)
+end
+
 end # module
