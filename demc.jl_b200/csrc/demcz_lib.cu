@@ -472,6 +472,7 @@ extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
                                          : M0 + (o.N_global * (int64_t)o.Ngeneration + o.K - 1) / o.K;   // src/demcz.jl:11
     if (cap < M0) cap = M0;
     if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
+    if (c->peers_open) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_archive: the peers hold mappings of the current archive; create a new context");
     if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
     CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->ZS * sizeof(float) + 256));      // + 8 x 8-byte segment flags written by the peers
     CU(c, cudaMemsetAsync(c->dZ + (size_t)cap * c->ZS, 0, 256, c->stream));
