@@ -385,12 +385,14 @@ def main():
             dp = lambda a: a.ctypes.data_as(C.POINTER(C.c_double))
             s._check(s.lib.demcz_get_state(s.ctx, dp(Xh), dp(lph)))
 
+            bufs = [(Xh, lph), (Xo, lpo)]
+
             def e2e_step():
-                s._check(s.lib.demcz_set_state(s.ctx, dp(Xh), dp(lph)))                       # H2D: population + log-objective
+                (xi, li), (xo, lo) = bufs                                                     # this step's input / output host arrays
+                s._check(s.lib.demcz_set_state(s.ctx, dp(xi), dp(li)))                       # H2D: population + log-objective
                 s.run(gps)
-                s._check(s.lib.demcz_get_state(s.ctx, dp(Xo), dp(lpo)))                       # D2H: new population + log-objective
-                Xh[...] = Xo
-                lph[...] = lpo
+                s._check(s.lib.demcz_get_state(s.ctx, dp(xo), dp(lo)))                       # D2H: new population + log-objective
+                bufs.reverse()                                                                # the result is the next step's input
 
             for _ in range(warmup):
                 e2e_step()
