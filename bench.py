@@ -30,6 +30,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
+# rank 0 prints exactly ONE line on stdout: keep NCCL's banner / debug output off it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 
 
 # ------------------------------------------------------------------------------------------------
