@@ -11,9 +11,9 @@ using namespace demcz;
 
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
-constexpr int LD = 20, WARPS = 4;
+constexpr int LD = 20;
 
-template <int MINB, int OPT>
+template <int MINB, int OPT, int WARPS = 4>
 float run_variant(StepArgs a, const std::vector<float>& Wfull, const std::vector<float>& mu, int reps, double* checksum)
 {
     using MP = MvnParams<LD>;
@@ -51,8 +51,8 @@ float run_variant(StepArgs a, const std::vector<float>& Wfull, const std::vector
     CK(cudaMemcpy(lp.data(), a.logp, a.N * 4, cudaMemcpyDeviceToHost));
     double cs = 0; for (float v : lp) cs += v;
     *checksum = cs;
-    printf("OPT=%2d (Wsmem=%d jmajor=%d idxvec=%d s2smem=%d) MINB=%d occ=%d blocks/SM : %8.2f us/launch  checksum %.6e\n", OPT,
-           !!(OPT & 1), !!(OPT & 2), !!(OPT & 4), !!(OPT & 8), MINB, occ, 1e3f * ms / reps, cs);
+    printf("OPT=%2d (Wsmem=%d jmajor=%d idxvec=%d s2smem=%d) WARPS=%d MINB=%d occ=%d blocks/SM N=%d : %8.2f us/launch  checksum %.6e\n", OPT,
+           !!(OPT & 1), !!(OPT & 2), !!(OPT & 4), !!(OPT & 8), WARPS, MINB, occ, a.N, 1e3f * ms / reps, cs);
     fflush(stdout);
     return ms / reps;
 }
@@ -141,6 +141,11 @@ int main(int argc, char** argv)
     double cs;
     const int reps = 20;
 #define RUN(MINB, OPT) reset(); run_variant<MINB, OPT>(a, W, mu, reps, &cs);
-    RUN(4, 1) RUN(4, 0) RUN(4, 1 + 16 + 32)
+    RUN(4, 0)
+    reset(); run_variant<8, 0, 2>(a, W, mu, reps, &cs);
+    reset(); run_variant<2, 0, 8>(a, W, mu, reps, &cs);
+    reset(); run_variant<4, 48>(a, W, mu, reps, &cs);
+    { StepArgs b = a; b.N = 65536; reset(); run_variant<4, 48>(b, W, mu, reps, &cs); reset(); run_variant<4, 0>(b, W, mu, reps, &cs); }
+    { StepArgs b = a; b.N = 32768; reset(); run_variant<4, 48>(b, W, mu, reps, &cs); }
     return 0;
 }
