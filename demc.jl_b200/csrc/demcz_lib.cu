@@ -236,12 +236,13 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     using SL = StageLayout<LD>;
     auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt>;
     const size_t smem = (size_t)kWarps * 2 * SL::FLOATS * sizeof(float);
-    static bool configured = false;       // per instantiation
-    if (!configured) {
+    static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
+    const int dev = c->device & 63;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured = true;
+        configured[dev] = true;
     }
     const int threads = kWarps * 32;
     const int grid = (a.N + threads - 1) / threads;

@@ -542,11 +542,12 @@ cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, 
 {
     auto kern = linreg_ssr_kernel<KB, TILE_N, STAGES, TERMS>;
     constexpr int smem = SsrSmem<KB, TILE_N, STAGES>::TOTAL;
-    static bool configured = false;
-    if (!configured) {
+    static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
+    const int dev = c->device & 63;
+    if (!configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
         if (e != cudaSuccess) return e;
-        configured = true;
+        configured[dev] = true;
     }
     const int units = CT * s->R;
     const int grid = std::min(units, s->sms);

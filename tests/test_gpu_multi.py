@@ -77,3 +77,31 @@ def test_two_gpus_reproduce_one_gpu_bitwise(sync_mode, p2p):
         np.testing.assert_array_equal(o[2], Z1)            # replicated archive, identical on every rank
         np.testing.assert_allclose(o[4], rhat1, rtol=1e-6)  # all-reduced Rhat (summation order differs)
     assert sum(o[3]["accepted"] for o in out) == info1["accepted"]
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+def test_two_gpus_wide_rows_and_linreg_bitwise():
+    # (a) d = 24: > 48 KB of dynamic shared memory per CTA — kernel attributes must be set on every device
+    d, N = 24, 256
+    S = 0.5 * np.ones((d, d)) + 0.5 * np.eye(d)
+    mu = np.linspace(0, 1, d)
+    Z0 = np.random.default_rng(1).normal(size=(2 * N, d))
+    kw = dict(K=4, Ngeneration=16, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.38, seed=3, store_chain=False)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, device=0, **kw) as s:
+        s.set_archive(Z0); s.run(); X1, lp1 = s.get_state(); Z1 = s.get_archive()
+    out = _run_sharded(lambda: DEMC.MvNormalLogpdf(mu, S), d, Z0, N, 2, p2p=True, **kw)
+    np.testing.assert_array_equal(np.concatenate([o[0] for o in out]), X1)
+    np.testing.assert_array_equal(out[1][2], Z1)
+    # (b) the tcgen05 linreg path, chains sharded, X replicated
+    rng = np.random.default_rng(2)
+    n, p = 3000, 9
+    X = np.ones((n, p)); X[:, 1:] = rng.normal(size=(n, p - 1)); beta = 1 + 3 * rng.random(p); y = X @ beta + rng.normal(size=n)
+    bols = np.linalg.solve(X.T @ X, X.T @ y)
+    Z0 = bols + 0.05 * rng.normal(size=(2 * N, p))
+    kw = dict(K=5, Ngeneration=15, blockindex=[list(range(p))], eps_scale=1e-5 * np.ones(p), γ=2.0, seed=5, store_chain=False)
+    with DEMC.Sampler(DEMC.LinRegLoglik(X, y), p, N=N, device=0, **kw) as s:
+        s.set_archive(Z0); s.run(); X1, lp1 = s.get_state(); Z1 = s.get_archive()
+    out = _run_sharded(lambda: DEMC.LinRegLoglik(X, y), p, Z0, N, 2, p2p=True, sync_mode="strict", **kw)
+    np.testing.assert_array_equal(np.concatenate([o[0] for o in out]), X1)
+    np.testing.assert_array_equal(np.concatenate([o[1] for o in out]), lp1)
+    np.testing.assert_array_equal(out[0][2], Z1)
