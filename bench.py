@@ -230,7 +230,7 @@ def measure_tf32_peak():
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=None,
@@ -264,6 +264,8 @@ def main():
         return dict(workload=w["name"], chains_per_gpu=w["chains_per_gpu"], chains_total=w["chains_per_gpu"] * max(world, 1),
                generations_per_step=gps, K=K, Nblocks=len(w["blocks"]), archive_rows_initial=w["archive_rows"],
                archive="replicated, ring buffer",
+               arithmetic=("FP32-equivalent: 3xTF32 tensor-core products, FP32 accumulate per 192-row tile, FP64 sums, FP64 log-objective"
+                           if w["kind"] == "linreg" else "FP32 state, archive and log-density"),
                l2=("X_hi + X_lo (2 x 4 n p bytes) > L2 (126 MB) and re-streamed every generation; no flush needed" if w["kind"] == "linreg"
                    else "archive > L2 (126 MB): random gathers miss L2; no flush needed"),
                sync_mode=args.sync,
@@ -464,7 +466,7 @@ def main():
         return dict(metric="chain-updates/s", value=value, unit="chain-updates/s", n_gpus=world, steps=steps, warmup=warmup,
                     ms_per_step=dev_ms / steps, wall_ms_per_step=wall_ms / steps, higher_is_better=True, scaling="weak",
                     vs_baseline=None,
-                    dtype="f32 (linreg: 3xTF32 products, FP32 accumulate, FP64 sums)" if w["kind"] == "linreg" else "f32",
+                    dtype="f32",
                     data="synthetic", config=cfg, clocks=clk, e2e=e2e, gpu_launches=launches, roofline=roof, cpu_baseline=cpu,
                     accepted_fraction=acc_frac, proposals_per_s=value * len(w["blocks"]))
 
