@@ -432,6 +432,8 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * ZS);
 #pragma unroll
             for (int c = 0; c < C; ++c) dst[c] = make_float4(x2[2 * c].x, x2[2 * c].y, x2[2 * c + 1].x, x2[2 * c + 1].y);
+            // complete the last 32-byte sector with slot padding: whole sectors need no read-modify-write fill in L2
+            if (C % 2 == 1 && C < CP) dst[C] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
         if (ACC) {
 #pragma unroll

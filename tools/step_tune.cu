@@ -142,10 +142,8 @@ int main(int argc, char** argv)
     const int reps = 20;
 #define RUN(MINB, OPT) reset(); run_variant<MINB, OPT>(a, W, mu, reps, &cs);
     RUN(4, 0)
-    reset(); run_variant<8, 0, 2>(a, W, mu, reps, &cs);
-    reset(); run_variant<2, 0, 8>(a, W, mu, reps, &cs);
-    reset(); run_variant<4, 48>(a, W, mu, reps, &cs);
-    { StepArgs b = a; b.N = 65536; reset(); run_variant<4, 48>(b, W, mu, reps, &cs); reset(); run_variant<4, 0>(b, W, mu, reps, &cs); }
-    { StepArgs b = a; b.N = 32768; reset(); run_variant<4, 48>(b, W, mu, reps, &cs); }
+    { StepArgs b = a; b.Zw = Z; b.append_row0 = 1000; reset(); printf("with append: "); run_variant<4, 0>(b, W, mu, reps, &cs); }
+    { StepArgs b = a; b.Mdraw = (uint32_t)(M0 / 2); reset(); printf("draw from half: "); run_variant<4, 0>(b, W, mu, reps, &cs); }
+    { StepArgs b = a; b.hist = nullptr; b.S1 = S1; reset(); printf("accept-heavy state: "); for (int k = 0; k < 20; ++k) (&b.eps2[0].x)[k] = 0.5f; run_variant<4, 0>(b, W, mu, reps, &cs); }
     return 0;
 }
