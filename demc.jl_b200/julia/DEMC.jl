@@ -9,8 +9,9 @@
 module DEMC
 
 using Libdl
+using LinearAlgebra: I
 
-const libdemcz = Ref{String}(get(ENV, "DEMCZ_LIB", joinpath(@__DIR__, "..", "libdemcz_cuda.so")))
+const libdemcz = get(ENV, "DEMCZ_LIB", joinpath(@__DIR__, "..", "libdemcz_cuda.so"))   # const global: a valid ccall library name
 
 # ---- struct MC / DEMCopt: verbatim field names and defaults (src/DEMC.jl:10-43) ---------------------------
 struct MC
@@ -55,7 +56,6 @@ struct LinRegLoglik <: GPULikelihood            # -0.5*sum((y .- X*b).^2)     (t
     X::Matrix{Float64}
     y::Vector{Float64}
 end
-using LinearAlgebra: I
 
 # ---- demcz_opts (include/demcz.h), field for field ---------------------------------------------------------
 struct COpts
@@ -79,13 +79,13 @@ end
 
 function check(ctx, rc)
     rc == 0 && return
-    msg = unsafe_string(ccall((:demcz_last_error, libdemcz[]), Cstring, (Ptr{Cvoid},), ctx))
+    msg = unsafe_string(ccall((:demcz_last_error, libdemcz), Cstring, (Ptr{Cvoid},), ctx))
     error("libdemcz_cuda: $rc: $msg")
 end
 
-register(ctx, l::MvNormalLogpdf) = ccall((:demcz_set_likelihood_mvnormal, libdemcz[]), Cint,
+register(ctx, l::MvNormalLogpdf) = ccall((:demcz_set_likelihood_mvnormal, libdemcz), Cint,
     (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32), ctx, length(l.μ), l.μ, l.Σ, l.drop_constant)
-register(ctx, l::LinRegLoglik) = ccall((:demcz_set_likelihood_linreg, libdemcz[]), Cint,
+register(ctx, l::LinRegLoglik) = ccall((:demcz_set_likelihood_linreg, libdemcz), Cint,
     (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}), ctx, size(l.X, 1), size(l.X, 2), l.X, l.y)
 register(ctx, f) = throw(ArgumentError("logobj must be a registered GPU likelihood (MvNormalLogpdf, QuadraticLogobj, LinRegLoglik); closures are not supported and there is no CPU fallback"))
 
@@ -104,40 +104,40 @@ function run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale
                   (anneal && get(adaptγ, "adapt", false)), get(adaptγ, "minγ", 0.1), get(adaptγ, "maxγ", 4.0), get(adaptγ, "adapt_every", 500),
                   seed, gen_offset, store_chain, 0, 0, 0, 0, 0, 1, N, 0, 0, 0)
         ctxref = Ref{Ptr{Cvoid}}(C_NULL)
-        rc = ccall((:demcz_create, libdemcz[]), Cint, (Ref{Ptr{Cvoid}}, Ref{COpts}, Cint), ctxref, Ref(o), device)
-        rc == 0 || error("demcz_create: " * unsafe_string(ccall((:demcz_last_error, libdemcz[]), Cstring, (Ptr{Cvoid},), C_NULL)))
+        rc = ccall((:demcz_create, libdemcz), Cint, (Ref{Ptr{Cvoid}}, Ref{COpts}, Cint), ctxref, Ref(o), device)
+        rc == 0 || error("demcz_create: " * unsafe_string(ccall((:demcz_last_error, libdemcz), Cstring, (Ptr{Cvoid},), C_NULL)))
     end
     ctx = ctxref[]
     try
         check(ctx, register(ctx, logobj))
         Z64 = Matrix{Float64}(Zmat)
-        check(ctx, ccall((:demcz_set_archive, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx, Z64, size(Z64, 1)))
+        check(ctx, ccall((:demcz_set_archive, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx, Z64, size(Z64, 1)))
         if prevrun !== nothing                                       # src/demcz.jl:20-21
-            check(ctx, ccall((:demcz_set_state, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx,
+            check(ctx, ccall((:demcz_set_state, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx,
                              Matrix{Float64}(prevrun.Xcurrent), Vector{Float64}(prevrun.log_objcurrent)))
         end
         if anneal && temperaturefun !== tempbaseline
             T = Float64[temperaturefun(ig, Ngeneration, T0, TN) for ig in 1:Ngeneration]
-            check(ctx, ccall((:demcz_set_temperature_table, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx, T, length(T)))
+            check(ctx, ccall((:demcz_set_temperature_table, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64), ctx, T, length(T)))
         end
         info = Ref(CRunInfo(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0))
-        check(ctx, ccall((:demcz_run, libdemcz[]), Cint, (Ptr{Cvoid}, Int64, Ref{CRunInfo}), ctx, 0, info))
+        check(ctx, ccall((:demcz_run, libdemcz), Cint, (Ptr{Cvoid}, Int64, Ref{CRunInfo}), ctx, 0, info))
         G = Int(info[].generations_total)
         chain = zeros(N, d, store_chain ? G : 0); log_obj = zeros(N, store_chain ? G : 0)
-        store_chain && G > 0 && check(ctx, ccall((:demcz_get_chain, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, chain, log_obj))
+        store_chain && G > 0 && check(ctx, ccall((:demcz_get_chain, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, chain, log_obj))
         X = zeros(N, d); lp = zeros(N)
-        check(ctx, ccall((:demcz_get_state, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, X, lp))
+        check(ctx, ccall((:demcz_get_state, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, X, lp))
         M = Ref{Int64}(0)
-        check(ctx, ccall((:demcz_get_archive, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), ctx, C_NULL, M))
+        check(ctx, ccall((:demcz_get_archive, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), ctx, C_NULL, M))
         Zout = zeros(M[], d)
-        check(ctx, ccall((:demcz_get_archive, libdemcz[]), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), ctx, Zout, M))
+        check(ctx, ccall((:demcz_get_archive, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ref{Int64}), ctx, Zout, M))
         mc = MC(chain, log_obj, X, lp)
         if prevrun !== nothing                                       # src/demcz.jl:59
             mc = MC(cat(prevrun.chain, mc.chain, dims=3), cat(prevrun.log_obj, mc.log_obj, dims=2), mc.Xcurrent, mc.log_objcurrent)
         end
         return mc, Zout
     finally
-        ccall((:demcz_destroy, libdemcz[]), Cvoid, (Ptr{Cvoid},), ctx)
+        ccall((:demcz_destroy, libdemcz), Cvoid, (Ptr{Cvoid},), ctx)
     end
 end
 
