@@ -274,6 +274,13 @@ class Sampler:
         self._check(self.lib.demcz_get_moments(self.ctx, _dp(mean), _dp(cov)))
         return mean, cov
 
+    def get_archive_moments(self, first_row, n_rows):
+        """mean / covariance of archive rows [first_row, first_row + n_rows): mean_cov_chain of the K-thinned history."""
+        mean = np.zeros(self.d)
+        cov = np.zeros((self.d, self.d))
+        self._check(self.lib.demcz_get_archive_moments(self.ctx, int(first_row), int(n_rows), _dp(mean), _dp(cov)))
+        return mean, cov
+
     def get_rhat(self):
         r = np.zeros(self.d)
         self._check(self.lib.demcz_get_rhat(self.ctx, _dp(r)))

@@ -166,6 +166,38 @@ __global__ void cov_kernel(const float* __restrict__ X, int n, int ldx, int d, c
     if (threadIdx.x == 0) atomicAdd(&cov[k1 * d + k2], s);
 }
 
+// archive rows (row-major slots, ring) -> per-column sums / centred cross products, FP64.  grid: (blocks, d) / (blocks, d*d)
+__global__ void rows_colsum_kernel(const float* __restrict__ Z, long long row0, long long n, long long zstart, long long zcap,
+                                   int ZS, double* __restrict__ sums)
+{
+    __shared__ double sm[32];
+    const int k = blockIdx.y;
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long p = zstart + row0 + i;
+        if (p >= zcap) p -= zcap;
+        s += Z[p * ZS + k];
+    }
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) atomicAdd(&sums[k], s);
+}
+
+__global__ void rows_cov_kernel(const float* __restrict__ Z, long long row0, long long n, long long zstart, long long zcap,
+                                int ZS, int d, const double* __restrict__ mean, double* __restrict__ cov)
+{
+    __shared__ double sm[32];
+    const int k1 = blockIdx.y / d, k2 = blockIdx.y % d;
+    const double m1 = mean[k1], m2 = mean[k2];
+    double s = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long p = zstart + row0 + i;
+        if (p >= zcap) p -= zcap;
+        s += ((double)Z[p * ZS + k1] - m1) * ((double)Z[p * ZS + k2] - m2);
+    }
+    s = block_sum(s, sm);
+    if (threadIdx.x == 0) atomicAdd(&cov[k1 * d + k2], s);
+}
+
 // Gelman-Rubin partial sums over the local chain-halves (Rhat_gelman, src/utils.jl:2-20):
 //   part[0*d+k] += sum_j mean_j    part[1*d+k] += sum_j mean_j^2    part[2*d+k] += sum_j S1_j^2
 // with mean_j = shift + S1_j/n.  Warp-shuffle -> block -> one FP64 atomic per block.
@@ -956,6 +988,33 @@ extern "C" int demcz_get_moments(demcz_ctx* c, double* mean, double* cov)
     CU(c, cudaStreamSynchronize(c->stream));
     if (mean) for (int k = 0; k < d; ++k) mean[k] = h[k];
     if (cov) for (int t = 0; t < d * d; ++t) cov[t] = h[d + t] / (double)c->o.N_global;
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_archive_moments(demcz_ctx* c, int64_t first_row, int64_t n_rows, double* mean, double* cov)
+{
+    CHECK_CTX(c);
+    if (!c->archive_set) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_archive_moments: no archive");
+    const int64_t rows = std::min<int64_t>(c->M, c->zcap);
+    if (first_row < 0 || n_rows < 1 || first_row + n_rows > rows)
+        return demcz_fail(c, DEMCZ_ERR_INVALID, "get_archive_moments: rows [%lld, %lld) outside the %lld valid rows", (long long)first_row,
+                          (long long)(first_row + n_rows), (long long)rows);
+    const int d = c->o.d;
+    const int64_t zstart = c->M > c->zcap ? c->M % c->zcap : 0;
+    double* sums = c->d_scratch;            // [d] sums, [d] mean, [d*d] cov
+    double* dmean = sums + d;
+    double* dcov = dmean + d;
+    CU(c, cudaMemsetAsync(sums, 0, (size_t)(2 * d + d * d) * sizeof(double), c->stream));
+    const int blocks = (int)std::min<int64_t>((n_rows + 255) / 256, 256);
+    rows_colsum_kernel<<<dim3(blocks, d), 256, 0, c->stream>>>(c->dZ, first_row, n_rows, zstart, c->zcap, c->ZS, sums);
+    shift_from_sums_kernel<<<1, 64, 0, c->stream>>>(sums, d, 1.0 / (double)n_rows, nullptr, dmean);
+    rows_cov_kernel<<<dim3(blocks, d * d), 256, 0, c->stream>>>(c->dZ, first_row, n_rows, zstart, c->zcap, c->ZS, d, dmean, dcov);
+    CU(c, cudaGetLastError());
+    std::vector<double> h((size_t)d + d * d);
+    CU(c, cudaMemcpyAsync(h.data(), dmean, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    if (mean) for (int k = 0; k < d; ++k) mean[k] = h[k];
+    if (cov) for (int t = 0; t < d * d; ++t) cov[t] = h[d + t] / (double)n_rows;
     return DEMCZ_OK;
 }
 

@@ -143,6 +143,10 @@ int demcz_get_state(demcz_ctx* ctx, double* X, double* logp);            /* Xcur
 int demcz_get_archive(demcz_ctx* ctx, double* Z, int64_t* M);
 /* population mean / covariance of Xcurrent (1/N normalisation, cf. mean_cov_chain src/utils.jl:96-106) */
 int demcz_get_moments(demcz_ctx* ctx, double* mean, double* cov);
+/* mean / covariance (1/n normalisation) of archive rows [first_row, first_row + n_rows) in logical order.  The rows
+ * appended during a run are the population every K-th generation, so this is mean_cov_chain (src/utils.jl:96-106) of
+ * the K-thinned history without keeping MC.chain: the posterior summary for runs with store_chain = 0. */
+int demcz_get_archive_moments(demcz_ctx* ctx, int64_t first_row, int64_t n_rows, double* mean, double* cov);
 /* last split-Rhat vector (Rhat_gelman, src/utils.jl:2-20), d values */
 int demcz_get_rhat(demcz_ctx* ctx, double* rhat);
 /* per-chain count of generations (2..G of this context) whose log-objective changed:

@@ -256,3 +256,25 @@ def test_zero_generations_and_state_only():
         X, lp = s.get_state()
         np.testing.assert_array_equal(X, _z0(20, d)[-N:].astype(np.float32).astype(np.float64))
         assert s.get_archive().shape == (20, d)
+
+
+def test_archive_moments_are_mean_cov_of_thinned_history():
+    # rows appended during the run = population every K-th generation -> mean_cov_chain (src/utils.jl:96-106) of the
+    # K-thinned chain, available without MC.chain; checked against the stored history and through the ring buffer
+    d, N, K, G = 5, 64, 5, 60
+    mu, S = example_normpdf_target(d)
+    for cap in (0, 500):
+        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=K, Ngeneration=G, blockindex=[list(range(d))],
+                          eps_scale=1e-5 * np.ones(d), γ=2.38, archive_capacity=cap, seed=4) as s:
+            s.set_archive(_z0(100, d))
+            s.run()
+            chain, _ = s.get_chain()
+            Z = s.get_archive()
+            n_new = N * 6                                  # the last 6 appended segments
+            m, C = s.get_archive_moments(Z.shape[0] - n_new, n_new)
+            with pytest.raises(_lib.DemczError):
+                s.get_archive_moments(Z.shape[0] - 10, 11)
+        thinned = chain[:, :, K - 1::K][:, :, -6:]
+        mref, Cref = DEMC.mean_cov_chain(thinned)
+        np.testing.assert_allclose(m, mref, rtol=1e-9, atol=1e-12)
+        np.testing.assert_allclose(C, Cref, rtol=1e-7, atol=1e-12)
