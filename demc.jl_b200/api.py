@@ -167,7 +167,7 @@ class Sampler:
         o.anneal, o.autostop, o.autostop_every, o.autostop_Rhat = int(anneal), int(autostop), int(autostop_every), float(autostop_Rhat)
         o.adapt, o.min_gamma, o.max_gamma, o.adapt_every = int(adapt), float(min_gamma), float(max_gamma), int(adapt_every)
         o.seed, o.gen_offset = int(seed) & (2**64 - 1), int(gen_offset)
-        o.store_chain = int(store_chain)
+        o.store_chain = 2 if store_chain == "stream" else int(bool(store_chain))
         o.init_mode = {"last_N_of_Z": 0, "ref_serial_zeros": 1}[init_mode]
         o.archive_capacity = int(archive_capacity)
         o.trace, o.profile = int(trace), int(profile)

@@ -37,8 +37,18 @@ struct demcz_ctx {
     int64_t M = 0;              // rows appended so far (valid rows = min(M, zcap))
     float* dT = nullptr;        // temperature table
     std::vector<float> hT;      // its host copy (the linreg path passes T by value)
-    float* dhist = nullptr;     // [G][d][N]
+    float* dhist = nullptr;     // [G][d][N]   (store_chain = 1: history resident on the device)
     float* dlphist = nullptr;   // [G][N]
+    // store_chain = 2: history streamed to pinned host memory, one launch's slice at a time (double-buffered on the
+    // device, copied on its own stream under the next launches)
+    float* hs_dx[2] = {nullptr, nullptr};        // [slice_gens][d][N]
+    void* hs_dlp[2] = {nullptr, nullptr};        // [slice_gens][N] float (closed-form path) or double (linreg)
+    float* hs_hx = nullptr;                      // pinned [G][d][N]
+    void* hs_hlp = nullptr;                      // pinned [G][N]
+    size_t hs_lp_elem = 0;
+    int64_t hs_slice_gens = 0, hs_launches = 0;
+    cudaStream_t hs_stream = nullptr;
+    cudaEvent_t hs_ev_k[2] = {nullptr, nullptr}, hs_ev_c[2] = {nullptr, nullptr};
     uint32_t* tr_r1 = nullptr; uint32_t* tr_r2 = nullptr; float* tr_u = nullptr; float* tr_xprop = nullptr;
     float* tr_lpprop = nullptr; uint8_t* tr_acc = nullptr;
     int* d_chain_changed = nullptr;
@@ -85,6 +95,10 @@ struct demcz_ctx {
 int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
 int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart);
 int demcz_archive_appended(demcz_ctx* c);
+// history destination of the launch covering generations [g, g + n_gens) (0-based): pointers such that index (grel - 1)
+// with grel = g + 1 .. g + n_gens is valid; lp elements are float (closed-form path) or double (linreg)
+int demcz_hist_begin(demcz_ctx* c, int64_t g, int n_gens, float** hist, void** lphist);
+int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens);
 
 // demcz_comm.cu — no-ops when world == 1
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);

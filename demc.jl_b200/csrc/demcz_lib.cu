@@ -412,7 +412,7 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
         alloc((void**)&c->dS2, (size_t)2 * o->d * sizeof(double));
         alloc((void**)&c->dshift, (size_t)o->d * sizeof(float));
     }
-    if (o->store_chain && o->Ngeneration > 0) {
+    if (o->store_chain == 1 && o->Ngeneration > 0) {
         alloc((void**)&c->dhist, (size_t)o->Ngeneration * o->d * o->N * sizeof(float));
         alloc((void**)&c->dlphist, (size_t)o->Ngeneration * o->N * sizeof(float));
     }
@@ -449,6 +449,15 @@ extern "C" void demcz_destroy(demcz_ctx* c)
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_xchg) cudaEventDestroy(ev);
+    for (int i = 0; i < 2; ++i) {
+        if (c->hs_dx[i]) cudaFree(c->hs_dx[i]);
+        if (c->hs_dlp[i]) cudaFree(c->hs_dlp[i]);
+        if (c->hs_ev_k[i]) cudaEventDestroy(c->hs_ev_k[i]);
+        if (c->hs_ev_c[i]) cudaEventDestroy(c->hs_ev_c[i]);
+    }
+    if (c->hs_hx) cudaFreeHost(c->hs_hx);
+    if (c->hs_hlp) cudaFreeHost(c->hs_hlp);
+    if (c->hs_stream) cudaStreamDestroy(c->hs_stream);
     if (c->ev_run[0]) { cudaEventDestroy(c->ev_run[0]); cudaEventDestroy(c->ev_run[1]); }
     if (c->stream) cudaStreamDestroy(c->stream);
     delete c;
@@ -661,6 +670,56 @@ int demcz_archive_appended(demcz_ctx* c)
     return DEMCZ_OK;
 }
 
+int demcz_hist_begin(demcz_ctx* c, int64_t g, int n_gens, float** hist, void** lphist)
+{
+    const demcz_opts& o = c->o;
+    *hist = nullptr; *lphist = nullptr;
+    if (!o.store_chain || o.Ngeneration <= 0) return DEMCZ_OK;
+    const bool lin = c->lik_kind == DEMCZ_LIK_LINREG;
+    if (o.store_chain == 1) {
+        *hist = c->dhist;
+        *lphist = lin ? (void*)demcz_linreg_lphist(c) : (void*)c->dlphist;
+        return DEMCZ_OK;
+    }
+    // ---- streamed history ----------------------------------------------------------------------------------
+    const size_t dn = (size_t)o.d * o.N;
+    if (!c->hs_hx) {                                    // first launch: allocate (the likelihood kind is known by now)
+        c->hs_lp_elem = lin ? sizeof(double) : sizeof(float);
+        c->hs_slice_gens = std::max<int64_t>(1, std::min<int64_t>(o.K, o.Ngeneration));
+        for (int i = 0; i < 2; ++i) {
+            CU(c, cudaMalloc((void**)&c->hs_dx[i], (size_t)c->hs_slice_gens * dn * sizeof(float)));
+            CU(c, cudaMalloc(&c->hs_dlp[i], (size_t)c->hs_slice_gens * o.N * c->hs_lp_elem));
+            CU(c, cudaEventCreateWithFlags(&c->hs_ev_k[i], cudaEventDisableTiming));
+            CU(c, cudaEventCreateWithFlags(&c->hs_ev_c[i], cudaEventDisableTiming));
+        }
+        CU(c, cudaHostAlloc((void**)&c->hs_hx, (size_t)o.Ngeneration * dn * sizeof(float), cudaHostAllocDefault));
+        CU(c, cudaHostAlloc(&c->hs_hlp, (size_t)o.Ngeneration * o.N * c->hs_lp_elem, cudaHostAllocDefault));
+        CU(c, cudaStreamCreateWithFlags(&c->hs_stream, cudaStreamNonBlocking));
+    }
+    if (n_gens > c->hs_slice_gens) return demcz_fail(c, DEMCZ_ERR_INVALID, "history slice of %d generations > %lld", n_gens, (long long)c->hs_slice_gens);
+    const int p = (int)(c->hs_launches & 1);
+    if (c->hs_launches >= 2) CU(c, cudaStreamWaitEvent(c->stream, c->hs_ev_c[p], 0));     // the slice's previous content is on the host
+    *hist = c->hs_dx[p] - (size_t)g * dn;                                                 // kernels index with (grel - 1) = g ..
+    *lphist = (char*)c->hs_dlp[p] - (size_t)g * o.N * c->hs_lp_elem;
+    return DEMCZ_OK;
+}
+
+int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens)
+{
+    const demcz_opts& o = c->o;
+    if (o.store_chain != 2 || !c->hs_hx) return DEMCZ_OK;
+    const size_t dn = (size_t)o.d * o.N;
+    const int p = (int)(c->hs_launches & 1);
+    CU(c, cudaEventRecord(c->hs_ev_k[p], c->stream));
+    CU(c, cudaStreamWaitEvent(c->hs_stream, c->hs_ev_k[p], 0));
+    CU(c, cudaMemcpyAsync(c->hs_hx + (size_t)g * dn, c->hs_dx[p], (size_t)n_gens * dn * sizeof(float), cudaMemcpyDeviceToHost, c->hs_stream));
+    CU(c, cudaMemcpyAsync((char*)c->hs_hlp + (size_t)g * o.N * c->hs_lp_elem, c->hs_dlp[p], (size_t)n_gens * o.N * c->hs_lp_elem,
+                          cudaMemcpyDeviceToHost, c->hs_stream));
+    CU(c, cudaEventRecord(c->hs_ev_c[p], c->hs_stream));
+    c->hs_launches += 1;
+    return DEMCZ_OK;
+}
+
 static cudaEvent_t pool_event(demcz_ctx* c, size_t i)
 {
     while (c->ev_pool.size() <= i) {
@@ -794,7 +853,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.Ttab = o.anneal ? c->dT : nullptr;
             a.Zw = append ? c->dZ : nullptr;
             a.append_row0 = (uint32_t)(c->M % c->zcap);
-            a.hist = c->dhist; a.lphist = c->dlphist;
+            { void* lph = nullptr; rc = demcz_hist_begin(c, g, n_gens, &a.hist, &lph); if (rc != DEMCZ_OK) return rc; a.lphist = (float*)lph; }
             a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
             a.tr_lpprop = c->tr_lpprop; a.tr_acc = c->tr_acc;
             a.chain_changed = c->d_chain_changed;
@@ -809,6 +868,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             CU(c, launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
+            rc = demcz_hist_end(c, g, n_gens);
+            if (rc != DEMCZ_OK) return rc;
         }
         c->proposals += (int64_t)n_gens * o.Nblocks * o.N;
 
@@ -847,6 +908,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     CU(c, cudaEventRecord(c->ev_run[1], c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
     if (c->comm_stream) CU(c, cudaStreamSynchronize(c->comm_stream));
+    if (c->hs_stream) CU(c, cudaStreamSynchronize(c->hs_stream));                 // streamed history is complete on the host
     if (stopped) c->stopped_by_rhat = true;
 
     if (info) {
@@ -913,9 +975,20 @@ static int d2h_as_f64(demcz_ctx* c, const float* src, size_t n, double* dst)
 extern "C" int demcz_get_chain(demcz_ctx* c, double* chain, double* log_obj)
 {
     CHECK_CTX(c);
-    if (!c->o.store_chain || !c->dhist) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: store_chain was 0");
     const size_t G = (size_t)c->g_done, N = c->o.N, d = c->o.d;
+    if (!c->o.store_chain) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: store_chain was 0");
     if (G == 0) return DEMCZ_OK;
+    if (c->o.store_chain == 2) {                        // streamed: FP32 (FP64 log-objective for linreg) pinned host copy -> caller's Float64
+        if (!c->hs_hx) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: no history yet");
+        CU(c, cudaStreamSynchronize(c->hs_stream));
+        if (chain) for (size_t t = 0; t < G * d * N; ++t) chain[t] = (double)c->hs_hx[t];
+        if (log_obj) {
+            if (c->hs_lp_elem == sizeof(double)) memcpy(log_obj, c->hs_hlp, G * N * sizeof(double));
+            else for (size_t t = 0; t < G * N; ++t) log_obj[t] = (double)((const float*)c->hs_hlp)[t];
+        }
+        return DEMCZ_OK;
+    }
+    if (!c->dhist) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: store_chain was 0");
     // device history is [g][k][chain] in FP32 == Julia's column-major N x d x G
     if (chain) { int rc = d2h_as_f64(c, c->dhist, G * d * N, chain); if (rc) return rc; }
     if (log_obj && c->lik_kind == DEMCZ_LIK_LINREG) {

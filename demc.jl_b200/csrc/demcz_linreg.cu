@@ -627,7 +627,7 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
     CUL(c, cudaMemsetAsync(s->Dlo, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
     CUL(c, cudaMemsetAsync(s->lp64, 0, (size_t)c->ldx * 2 * sizeof(double), c->stream));
-    if (o.store_chain && o.Ngeneration > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)o.Ngeneration * o.N * sizeof(double)));
+    if (o.store_chain == 1 && o.Ngeneration > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)o.Ngeneration * o.N * sizeof(double)));
 
     // ---- upload (FP64, as the caller holds it), split, OLS reference point -------------------------
     const int P1 = p + 1, npairs = P1 * P1;
@@ -779,6 +779,8 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
     const int CT = s->Npad / 128;
     uint32_t Mdraw = 0, zstart = 0;
     { int rc = demcz_archive_view(c, &Mdraw, &zstart); if (rc != DEMCZ_OK) return rc; }
+    float* hist = nullptr; void* lphist = nullptr;
+    { int rc = demcz_hist_begin(c, g, n_gens, &hist, &lphist); if (rc != DEMCZ_OK) return rc; }
     for (int gi = 0; gi < n_gens; ++gi) {
         const int64_t grel = g + gi + 1;
         for (int b = 0; b < o.Nblocks; ++b) {
@@ -822,7 +824,7 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
             q.count_run = (grel != 1) ? 1 : 0;
             q.count_win = (o.anneal && o.adapt && (grel - 1) % o.adapt_every == 0) ? 0 : 1;
-            q.hist = c->dhist; q.lphist = s->lphist64;
+            q.hist = hist; q.lphist = (double*)lphist;
             const bool do_append = append && gi == n_gens - 1;
             q.Zw = do_append ? c->dZ : nullptr; q.ZS = c->ZS;
             q.append_row0 = (uint32_t)(c->M % c->zcap); q.zcap = (uint32_t)c->zcap; q.chain_offset = (uint32_t)o.chain_offset;
@@ -832,5 +834,5 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             CUL(c, cudaGetLastError());
         }
     }
-    return DEMCZ_OK;
+    return demcz_hist_end(c, g, n_gens);
 }

@@ -72,7 +72,8 @@ typedef struct {
     uint64_t seed;              /* Philox key */
     int64_t gen_offset;         /* generations already run by earlier calls (prevrun): the Philox
                                    generation counter continues at gen_offset + 1 */
-    int32_t store_chain;        /* keep MC.chain / MC.log_obj (N x d x G) on the device */
+    int32_t store_chain;        /* MC.chain / MC.log_obj (N x d x G): 0 = not kept, 1 = resident on the device, 2 = streamed to pinned
+                                   host memory during the run (one launch's slice at a time, copied under the next launches) */
     int32_t init_mode;          /* DEMCZ_INIT_* */
     int64_t archive_capacity;   /* rows; 0 -> M0 + ceil(N_global*Ngeneration/K) (src/demcz.jl:11) */
     int32_t trace;              /* 1: record per-proposal r1,r2,u,xprop,lp_prop,accept (tests) */

@@ -278,3 +278,26 @@ def test_archive_moments_are_mean_cov_of_thinned_history():
         mref, Cref = DEMC.mean_cov_chain(thinned)
         np.testing.assert_allclose(m, mref, rtol=1e-9, atol=1e-12)
         np.testing.assert_allclose(C, Cref, rtol=1e-7, atol=1e-12)
+
+
+@pytest.mark.parametrize("kind", ["mvn", "linreg"])
+def test_streamed_history_equals_resident_history(kind):
+    # store_chain="stream" (demcz_opts.store_chain = 2): each launch's history slice goes to pinned host memory under
+    # the following launches; MC.chain / MC.log_obj must be identical to the device-resident history
+    rng = np.random.default_rng(12)
+    if kind == "mvn":
+        d = 5
+        mu, S = example_normpdf_target(d)
+        lo = DEMC.MvNormalLogpdf(mu, S)
+        Z0 = _z0(80, d)
+    else:
+        n, d = 900, 6
+        X = np.ones((n, d)); X[:, 1:] = rng.normal(size=(n, d - 1)); y = X @ (1 + rng.random(d)) + rng.normal(size=n)
+        lo = DEMC.LinRegLoglik(X, y)
+        Z0 = np.linalg.solve(X.T @ X, X.T @ y) + 0.05 * rng.normal(size=(80, d))
+    args = (40, 7, 33, 1, [list(range(d))], 1e-5 * np.ones(d), 2.2)
+    a, Za = DEMC.demcz_sample(lo, Z0, *args, verbose=False, store_chain=True)
+    b, Zb = DEMC.demcz_sample(lo, Z0, *args, verbose=True, print_step=5, store_chain="stream")     # verbose: chunked demcz_run calls
+    np.testing.assert_array_equal(a.chain, b.chain)
+    np.testing.assert_array_equal(a.log_obj, b.log_obj)
+    np.testing.assert_array_equal(Za, Zb)
