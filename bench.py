@@ -243,6 +243,9 @@ def main():
     ap.add_argument("--sync", default="overlap", choices=["strict", "overlap"],
                     help="strict: appended rows drawable at once (bit-identical to 1 GPU); overlap: one K-block later, exchange hidden under compute")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="p2p: own push kernel over peer-mapped archives; nccl: ncclAllGather")
+    ap.add_argument("--exchange-layout", default="auto", choices=["auto", "in_place", "packed"],
+                    help="p2p push: rows stored straight into the peers' padded slots, or packed through a staging ring and scattered "
+                         "by the receiver (fewer NVLink lines); auto = packed when slots have padding and more than 4 GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -270,7 +273,7 @@ def main():
                    else "archive > L2 (126 MB): random gathers miss L2; no flush needed"),
                sync_mode=args.sync,
                parallelism=(f"chains sharded x{world}; appended rows exchanged every K generations by "
-                            + ("our push kernel into peer-mapped archive replicas (NVLink), published by flag words" if args.exchange == "p2p" else "ncclAllGather")
+                            + (f"our push kernel into peer-mapped archive replicas (NVLink; layout {args.exchange_layout}), published by flag words" if args.exchange == "p2p" else "ncclAllGather")
                             + (", on a side stream under the next K-block" if args.sync == "overlap" else ", on the compute stream")))
 
     # ---------------------------------------------------------------- reference arm (CPU) -------
@@ -354,7 +357,7 @@ def main():
                                        Ngeneration=G_total, blockindex=w["blocks"], eps_scale=1e-5 * np.ones(d), γ=w["gamma"],
                                        anneal=w["anneal"], T0=2.0, TN=1e-4, autostop=w["autostop"], autostop_every=1000,
                                        autostop_Rhat=0.0, adapt=False, seed=31953150, store_chain=False, archive_capacity=cap,
-                                       sync_mode=args.sync)
+                                       sync_mode=args.sync, exchange_layout=args.exchange_layout)
         s.set_archive(Z0)
         del Z0
         if world > 1 and args.exchange == "p2p":

@@ -31,7 +31,7 @@ class Opts(C.Structure):
         ("store_chain", C.c_int32), ("init_mode", C.c_int32), ("archive_capacity", C.c_int64),
         ("trace", C.c_int32), ("profile", C.c_int32),
         ("rank", C.c_int32), ("world", C.c_int32), ("N_global", C.c_int64), ("chain_offset", C.c_int64),
-        ("sync_mode", C.c_int32), ("reserved", C.c_int32),
+        ("sync_mode", C.c_int32), ("exchange_layout", C.c_int32),
     ]
 
 

@@ -146,7 +146,7 @@ class Sampler:
                  autostop=False, autostop_every=1000, autostop_Rhat=1.05, adapt=False, min_gamma=0.1, max_gamma=4.0,
                  adapt_every=500, seed=31953150, gen_offset=0, store_chain=True, init_mode="last_N_of_Z",
                  archive_capacity=0, trace=False, profile=False, device=0, rank=0, world=1, N_global=None,
-                 chain_offset=0, sync_mode="strict"):
+                 chain_offset=0, sync_mode="strict", exchange_layout="auto"):
         _check_likelihood(logobj)
         self.lib = _lib.load()
         self.d, self.N = int(d), int(N)
@@ -175,6 +175,7 @@ class Sampler:
         o.N_global = self.N if N_global is None else int(N_global)
         o.chain_offset = int(chain_offset)
         o.sync_mode = {"strict": 0, "overlap": 1}[sync_mode]
+        o.exchange_layout = {"auto": 0, "in_place": 1, "packed": 2}[exchange_layout]
         self.opts = o
         self.Nblocks = len(blocks)
         self.ctx = C.c_void_p()

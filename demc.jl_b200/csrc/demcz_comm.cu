@@ -12,8 +12,8 @@
 // Every rank stores its N_local new rows (the 16-byte pieces that hold data, not the slot padding) straight
 // into the same slots of every peer's archive replica over NVLink/NVSwitch — the minimum bytes that must cross
 // the links (N_local * 16*ceil(d/4) bytes per peer), no staging buffer, no unpack pass — and a one-word NCCL
-// all-reduce is the cross-rank barrier that publishes the segment.  In overlap mode the push and the barrier run
-// on a high-priority side stream (with their own communicator) under the next K-block's step kernel.
+// flag word per rank in every peer's allocation publishes the segment.  In overlap mode the push runs on a
+// high-priority side stream under the next K-block's step kernel.
 #include "demcz_internal.h"
 #include <dlfcn.h>
 #include <unistd.h>
@@ -156,9 +156,16 @@ struct PeerPtrs { float* p[8]; };
 // (16 bytes each) of a slot cross the links.  A small persistent grid (a few CTAs are enough to saturate NVLink
 // with 16-byte stores) so that it shares the SMs with the step kernel it runs under.  When the last CTA is done —
 // all stores fenced at system scope — it publishes the segment: peer r's flag word [my rank] = seq.
+//
+// PACKED (DEMCZ_XCHG_PACKED): the destination is not the slot but `packed_base + 4 t` floats into the peer's
+// allocation — this rank's block of the staging ring, rows back to back.  NVLink moves whole 128-byte lines and a
+// partly written line costs a full one (tools/push_bench.cu: 5.2 G lines/s either way), so 80-byte rows of a
+// 128-byte slot cross the links 1.55x faster packed; the receiver scatters them (unpack_rows_kernel).
+template <bool PACKED>
 __global__ void __launch_bounds__(256)
 push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long long row0, int nrows, int ZS, int C,
-                 unsigned long long flag_off_floats, int my_rank, unsigned long long seq, unsigned int* done_counter)
+                 unsigned long long packed_base, unsigned long long flag_off_floats, int my_rank, unsigned long long seq,
+                 unsigned int* done_counter)
 {
     constexpr int U = 8;                         // independent 16-byte loads in flight per thread
     const long long total = (long long)nrows * C;
@@ -171,8 +178,9 @@ push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long 
             const long long t = t0 + u * stride;
             const long long row = t / C;
             const int piece = (int)(t - row * C);
-            off[u] = (size_t)(row0 + row) * ZS + piece * 4;
-            if (t < total) v[u] = __ldcg(reinterpret_cast<const float4*>(Zl + off[u]));
+            const size_t src = (size_t)(row0 + row) * ZS + piece * 4;
+            off[u] = PACKED ? (size_t)packed_base + (size_t)t * 4 : src;
+            if (t < total) v[u] = __ldcg(reinterpret_cast<const float4*>(Zl + src));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -190,6 +198,36 @@ push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long 
             unsigned long long* f = reinterpret_cast<unsigned long long*>(peers.p[threadIdx.x] + flag_off_floats) + my_rank;
             asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
         }
+    }
+}
+
+// Receiver side of the packed exchange: the other ranks' rows of one landed segment, staging ring -> row slots.
+// `stage`: the segment's buffer [N_global][4 C] floats; rows of this rank's own block [own0, own0 + n_own) are already
+// in place (written by the append).  An odd piece count gets its last 32-byte sector completed with slot padding,
+// like the append does (whole sectors need no read-modify-write fill in L2).
+__global__ void __launch_bounds__(256)
+unpack_rows_kernel(const float* __restrict__ stage, float* __restrict__ Zl, long long seg_row0, long long n_rows,
+                   long long own0, long long n_own, int ZS, int C, int CW)
+{
+    constexpr int U = 4;
+    const long long total = (n_rows - n_own) * CW;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * U) {
+        float4 v[U];
+        size_t dst[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long t = t0 + u * stride;
+            long long row = t / CW;
+            const int piece = (int)(t - row * CW);
+            if (row >= own0) row += n_own;
+            dst[u] = (size_t)(seg_row0 + row) * ZS + piece * 4;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (t < total && piece < C) v[u] = __ldcg(reinterpret_cast<const float4*>(stage + (size_t)row * (4 * C) + piece * 4));
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+            if (t0 + u * stride < total) *reinterpret_cast<float4*>(Zl + dst[u]) = v[u];
     }
 }
 
@@ -259,6 +297,10 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
         }
     }
     c->peers_open = true;
+    // every rank takes the same decision (same opts): pack when the slots have padding and the push would not hide
+    // under a K-block any more (8 GPUs: 7 x N rows per K-block at 5.2 G lines/s) — or when asked to
+    const int lay = c->o.exchange_layout;
+    c->xchg_packed = c->ZS != c->LD && (lay == DEMCZ_XCHG_PACKED || (lay == DEMCZ_XCHG_AUTO && c->o.world > 4));
     return DEMCZ_OK;
 }
 
@@ -284,9 +326,17 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
         const long long total = (long long)c->o.N * C;
         const int grid = (int)std::min<long long>(32, (total + 255) / 256);      // measured: 16..128 CTAs move the same bytes/s (link-bound)
         const unsigned long long seq = (unsigned long long)c->appends + 1;       // this is segment number `appends`
+        unsigned int* done = (unsigned int*)(c->d_barrier + (side ? 1 : 0));
         mark();
-        push_rows_kernel<<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C,
-                                               (unsigned long long)c->zcap * c->ZS, c->o.rank, seq, (unsigned int*)(c->d_barrier + (side ? 1 : 0)));
+        if (c->xchg_packed) {
+            const int buf = (int)(c->appends % kStageDepth);
+            const unsigned long long base = demcz_stage_off_floats(c) + ((size_t)buf * c->o.N_global + c->o.chain_offset) * c->LD;
+            push_rows_kernel<true><<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C, base,
+                                                         demcz_flag_off_floats(c), c->o.rank, seq, done);
+        } else {
+            push_rows_kernel<false><<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C, 0ull,
+                                                          demcz_flag_off_floats(c), c->o.rank, seq, done);
+        }
         if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "push_rows_kernel launch failed");
         mark();
         if (!side) return demcz_comm_wait_segment(c, (int64_t)seq);               // strict: publish before the next launch
@@ -321,8 +371,22 @@ int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n)
 int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg)
 {
     if (c->o.world == 1 || !c->peers_open || nseg <= 0) return DEMCZ_OK;
-    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(c->dZ + (size_t)c->zcap * c->ZS);
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(c->dZ + demcz_flag_off_floats(c));
     wait_flags_kernel<<<1, 32, 0, c->stream>>>(flags, c->o.world, c->o.rank, (unsigned long long)nseg);
     if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "wait_flags_kernel launch failed");
+    if (c->xchg_packed) {
+        // segment s was appended at M_base + s N_global; M and appends advance together (demcz_archive_appended)
+        const int64_t M_base = c->M - c->appends * c->o.N_global;
+        const int C = c->LD / 4, CP = c->ZS / 4, CW = C + ((C % 2 == 1 && C < CP) ? 1 : 0);
+        const long long total = (long long)(c->o.N_global - c->o.N) * CW;
+        const int grid = (int)std::min<long long>(148 * 4, (total + 256 * 4 - 1) / (256 * 4));
+        for (; c->unpacked < nseg; ++c->unpacked) {
+            const int64_t s = c->unpacked;
+            const float* stage = c->dZ + demcz_stage_off_floats(c) + (size_t)(s % kStageDepth) * c->o.N_global * c->LD;
+            unpack_rows_kernel<<<grid, 256, 0, c->stream>>>(stage, c->dZ, (M_base + s * c->o.N_global) % c->zcap, c->o.N_global,
+                                                            c->o.chain_offset, c->o.N, c->ZS, C, CW);
+            if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "unpack_rows_kernel launch failed");
+        }
+    }
     return DEMCZ_OK;
 }

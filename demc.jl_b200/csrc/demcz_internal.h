@@ -86,11 +86,22 @@ struct demcz_ctx {
     bool peers_open = false;
     int64_t appends = 0;                         // archive appends so far (overlap mode: visibility lags by one)
     int64_t vis_waited = 0;
+    bool xchg_packed = false;                    // DEMCZ_XCHG_PACKED in effect: rows travel densely through the staging ring
+    int64_t unpacked = 0;                        // packed exchange: segments 0 .. unpacked-1 have been scattered into the slots
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
 
     std::string err;
     int sticky = 0;
 };
+
+// One device allocation holds the archive and everything the peers write into, so that a single IPC handle maps it:
+//   [zcap row slots][8 x u64 segment flags, 256 B][staging ring: kStageDepth x N_global dense rows of LD floats]   (ring: world > 1)
+// Depth 4: a sender refills buffer s % 4 with segment s + 4 only after its K-block s + 4 started, which needed the
+// receiver's segment s + 2, which the receiver pushes after its K-block s + 2, which started after it unpacked segment s.
+constexpr int kStageDepth = 4;
+inline size_t demcz_flag_off_floats(const demcz_ctx* c) { return (size_t)c->zcap * c->ZS; }
+inline size_t demcz_stage_off_floats(const demcz_ctx* c) { return (demcz_flag_off_floats(c) + 64 + 31) / 32 * 32; }
+inline size_t demcz_stage_floats(const demcz_ctx* c) { return c->o.world > 1 ? (size_t)kStageDepth * c->o.N_global * c->LD : 0; }
 
 int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
 int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart);
@@ -102,7 +113,7 @@ int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens);
 
 // demcz_comm.cu — no-ops when world == 1
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);
-int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);
+int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);     // + packed exchange: scatters the landed segments into their slots
 int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n);
 int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);
 void demcz_comm_destroy_internal(demcz_ctx* c);

@@ -516,12 +516,14 @@ extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
     if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
     if (c->peers_open) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_archive: the peers hold mappings of the current archive; create a new context");
     if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
-    CU(c, cudaMalloc((void**)&c->dZ, (size_t)cap * c->ZS * sizeof(float) + 256));      // + 8 x 8-byte segment flags written by the peers
-    CU(c, cudaMemsetAsync(c->dZ + (size_t)cap * c->ZS, 0, 256, c->stream));
     c->zcap = cap;
+    // archive + segment flags written by the peers + staging ring of the packed exchange (demcz_internal.h)
+    CU(c, cudaMalloc((void**)&c->dZ, (demcz_stage_off_floats(c) + demcz_stage_floats(c)) * sizeof(float)));
+    CU(c, cudaMemsetAsync(c->dZ + demcz_flag_off_floats(c), 0, (demcz_stage_off_floats(c) - demcz_flag_off_floats(c)) * sizeof(float), c->stream));
     c->M = M0;
     c->appends = 0;
     c->vis_waited = 0;
+    c->unpacked = 0;
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, (size_t)M0 * o.d * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(stage, Z, (size_t)M0 * o.d * sizeof(double), cudaMemcpyHostToDevice, c->stream);

@@ -68,7 +68,7 @@ struct COpts
     store_chain::Int32; init_mode::Int32; archive_capacity::Int64
     trace::Int32; profile::Int32
     rank::Int32; world::Int32; N_global::Int64; chain_offset::Int64
-    sync_mode::Int32; reserved::Int32
+    sync_mode::Int32; exchange_layout::Int32
 end
 
 struct CRunInfo

@@ -46,6 +46,14 @@ enum { DEMCZ_INIT_LAST_N_OF_Z = 0, DEMCZ_INIT_REF_SERIAL_ZEROS = 1 };   /* SURVE
  * OVERLAP: they become drawable one K-block later, on every rank and for every world size (also 1), so that the
  * exchange of a segment runs under the next K-block's compute; results are still independent of the sharding. */
 enum { DEMCZ_SYNC_STRICT = 0, DEMCZ_SYNC_OVERLAP = 1 };
+/* How a rank's appended rows travel to the peers' archive replicas once demcz_comm_open_peers was called.  A row of
+ * d <= 32 floats sits in a power-of-two slot (32/64/128 bytes) and NVLink moves whole 128-byte lines (a partial
+ * line costs a full one: 5.2 G lines/s measured), so
+ *   IN_PLACE: stored straight into the peers' slots (no second pass; best while the push hides under compute),
+ *   PACKED  : stored densely into a staging ring next to each peer's archive (up to 1.6x fewer lines on the links)
+ *             and scattered into the slots by the receiver before the segment becomes drawable,
+ *   AUTO    : PACKED when slots have padding and world > 4, else IN_PLACE.  Results are identical either way. */
+enum { DEMCZ_XCHG_AUTO = 0, DEMCZ_XCHG_IN_PLACE = 1, DEMCZ_XCHG_PACKED = 2 };
 
 /* Mirror of DEMCopt (src/DEMC.jl:24-39) + the keyword arguments of demcz_sample (src/demcz.jl:9)
  * and demcz_anneal (src/demcz_anneal.jl:18), as a POD.  Field meaning == reference option of the
@@ -83,7 +91,7 @@ typedef struct {
     int64_t N_global;
     int64_t chain_offset;       /* global id of local chain 0 (Philox counter, archive row order) */
     int32_t sync_mode;          /* DEMCZ_SYNC_* */
-    int32_t reserved;
+    int32_t exchange_layout;    /* DEMCZ_XCHG_* (was reserved = 0 -> AUTO) */
 } demcz_opts;
 
 typedef struct {
