@@ -243,9 +243,9 @@ def main():
     ap.add_argument("--sync", default="overlap", choices=["strict", "overlap"],
                     help="strict: appended rows drawable at once (bit-identical to 1 GPU); overlap: one K-block later, exchange hidden under compute")
     ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"], help="p2p: own push kernel over peer-mapped archives; nccl: ncclAllGather")
-    ap.add_argument("--exchange-layout", default="auto", choices=["auto", "in_place", "packed"],
+    ap.add_argument("--exchange-layout", default="auto", choices=["auto", "in_place", "packed", "dense_slots"],
                     help="p2p push: rows stored straight into the peers' padded slots, or packed through a staging ring and scattered "
-                         "by the receiver (fewer NVLink lines); auto = packed when slots have padding and more than 4 GPUs")
+                         "by the receiver (fewer NVLink lines), or the archive keeps rows without slot padding (dense_slots); auto = dense_slots for more than 4 GPUs")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()

@@ -175,7 +175,7 @@ class Sampler:
         o.N_global = self.N if N_global is None else int(N_global)
         o.chain_offset = int(chain_offset)
         o.sync_mode = {"strict": 0, "overlap": 1}[sync_mode]
-        o.exchange_layout = {"auto": 0, "in_place": 1, "packed": 2}[exchange_layout]
+        o.exchange_layout = {"auto": 0, "in_place": 1, "packed": 2, "dense_slots": 3}[exchange_layout]
         self.opts = o
         self.Nblocks = len(blocks)
         self.ctx = C.c_void_p()

@@ -116,9 +116,17 @@ extern "C" int demcz_comm_init(demcz_ctx* c, const uint8_t id[128])
             cudaEventCreateWithFlags(&c->ev_vis[i], cudaEventDisableTiming) != cudaSuccess)
             return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: cudaEventCreate");
     }
-    if (cudaMalloc((void**)&c->d_barrier, 2 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(c->d_barrier, 0, 2 * sizeof(unsigned long long)) != cudaSuccess)
+    if (cudaMalloc((void**)&c->d_barrier, 4 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(c->d_barrier, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
         return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: barrier word");
+    // NCCL connects lazily at the first collective of a communicator (hundreds of ms): pay for it here, not inside
+    // the first Rhat / adaptγ reduction of a run
+    rc = a.AllReduce(c->d_barrier + 2, c->d_barrier + 2, 1, ncclUint64, ncclSum, comm, c->stream);
+    if (rc != ncclSuccess) return nccl_fail(c, "ncclAllReduce (warm-up)", rc);
+    if (cudaStreamSynchronize(c->stream) != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: warm-up sync");
+    rc = a.AllReduce(c->d_barrier + 3, c->d_barrier + 3, 1, ncclUint64, ncclSum, comm2, c->comm_stream);
+    if (rc != ncclSuccess) return nccl_fail(c, "ncclAllReduce (warm-up, side)", rc);
+    if (cudaStreamSynchronize(c->comm_stream) != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: warm-up sync");
     return DEMCZ_OK;
 }
 
@@ -297,10 +305,9 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
         }
     }
     c->peers_open = true;
-    // every rank takes the same decision (same opts): pack when the slots have padding and the push would not hide
-    // under a K-block any more (8 GPUs: 7 x N rows per K-block at 5.2 G lines/s) — or when asked to
+    // every rank takes the same decision (same opts); with dense slots (ZS == LD) the in-place push is already packed
     const int lay = c->o.exchange_layout;
-    c->xchg_packed = c->ZS != c->LD && (lay == DEMCZ_XCHG_PACKED || (lay == DEMCZ_XCHG_AUTO && c->o.world > 4));
+    c->xchg_packed = c->ZS != c->LD && lay == DEMCZ_XCHG_PACKED;
     return DEMCZ_OK;
 }
 

@@ -262,11 +262,11 @@ MvnParams<LD> make_params(const demcz_ctx* c, bool jmajor)
 // resident blocks per SM the register allocation is held to (4 warps per block)
 template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
 
-template <int LD, bool ACC, bool FULL>
+template <int LD, bool ACC, bool FULL, bool DENSE>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt>;
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE>;
     const size_t smem = (size_t)kWarps * 2 * SL::FLOATS * sizeof(float);
     static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
     const int dev = c->device & 63;
@@ -283,11 +283,20 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     return cudaGetLastError();
 }
 
+template <int LD, bool DENSE>
+cudaError_t launch_step_lay(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
+{
+    if (full) return acc ? launch_step_t<LD, true, true, DENSE>(c, a) : launch_step_t<LD, false, true, DENSE>(c, a);
+    return acc ? launch_step_t<LD, true, false, DENSE>(c, a) : launch_step_t<LD, false, false, DENSE>(c, a);
+}
+
 template <int LD>
 cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
-    if (full) return acc ? launch_step_t<LD, true, true>(c, a) : launch_step_t<LD, false, true>(c, a);
-    return acc ? launch_step_t<LD, true, false>(c, a) : launch_step_t<LD, false, false>(c, a);
+    if constexpr (zslot(LD) != LD) {            // dense slots (DEMCZ_XCHG_DENSE_SLOTS) only differ where the slot has padding
+        if (c->ZS == LD) return launch_step_lay<LD, true>(c, a, acc, full);
+    }
+    return launch_step_lay<LD, false>(c, a, acc, full);
 }
 
 cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
@@ -358,6 +367,8 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: inconsistent rank/world/N_global/chain_offset");
     if (o->autostop && (o->autostop_every < 4))
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: autostop_every must be >= 4");
+    if (o->exchange_layout < DEMCZ_XCHG_AUTO || o->exchange_layout > DEMCZ_XCHG_DENSE_SLOTS)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: exchange_layout %d", o->exchange_layout);
     if (o->anneal && o->adapt && o->adapt_every < 1)
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: adapt_every must be >= 1");
     for (int b = 0; b < o->Nblocks; ++b) {
@@ -386,6 +397,8 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
     c->gamma = o->gamma;
     c->LD = (o->d + 3) / 4 * 4;
     c->ZS = o->d <= DEMCZ_MAX_DIM ? zslot(c->LD) : c->LD;
+    // rows back to back instead of padded slots when the exchange rather than the gather bounds a K-block (demcz.h)
+    if (o->exchange_layout == DEMCZ_XCHG_DENSE_SLOTS || (o->exchange_layout == DEMCZ_XCHG_AUTO && o->world > 4)) c->ZS = c->LD;
     c->ldx = (o->N + 31) / 32 * 32;
     c->keys = make_philox_keys(o->seed);
     if (const char* gr = getenv("DEMCZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));

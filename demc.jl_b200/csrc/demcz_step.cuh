@@ -216,15 +216,20 @@ __device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ Wc, c
 }
 
 // FULL: a single block covering every column (the common case) — no per-column masks.
-template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT>
+// DENSE: archive rows back to back (slot = LD floats) instead of power-of-two slots.  The gather then pays for the
+// rows that straddle a 128-byte line (measured 1.39x the DRAM bytes per row for d = 20), but a rank's appended rows
+// are contiguous, so they cross NVLink as whole lines — the layout of choice when the exchange, not the gather,
+// bounds the K-block (8 GPUs).
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
     using SL = StageLayout<LD>;
     using MP = MvnParams<LD>;
-    constexpr int C = SL::C, LDS = SL::LDS, ZS = zslot(LD), CP = ZS / 4, RPI = 32 / CP, STAGES = 2, H = LD / 2;
+    constexpr int C = SL::C, LDS = SL::LDS, ZS = DENSE ? LD : zslot(LD), CP = ZS / 4, RPI = 32 / CP, STAGES = 2, H = LD / 2;
     constexpr bool W_SMEM = OPT & OPT_W_SMEM, JMAJOR = OPT & OPT_JMAJOR, IDX_VEC = OPT & OPT_IDX_VEC,
                    S2_SMEM = (OPT & OPT_S2_SMEM) && ACC;
+    static_assert(!(DENSE && IDX_VEC), "the vectorised index read needs 64 % RPI == 0");
     constexpr int NWC = JMAJOR ? MP::NW_COL : MP::NW_ROW;
     extern __shared__ __align__(16) float smem[];
     __shared__ unsigned int red_cnt[2];
@@ -274,9 +279,10 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     // lane -> (staged row, 16-byte piece of the row slot), lane-only so that the copy loop has compile-time
     // shared-memory offsets.  IDX_VEC: a lane group owns RPL consecutive staged rows (their indices are read
     // with LDS.128); otherwise copy instruction `it` covers rows it*RPI .. it*RPI+RPI-1.
-    constexpr int RPL = 64 / RPI;                       // copy instructions per stage
+    constexpr int RPL = (64 + RPI - 1) / RPI;           // copy instructions per stage
+    constexpr bool RAGGED = (64 % RPI) != 0;            // (dense slots) the last instruction covers fewer than RPI rows
     const int lrow = lane / CP, lpiece = lane % CP;
-    const bool pact = lpiece < C;
+    const bool pact = lpiece < C && lrow < RPI;         // (dense slots) 32 % CP lanes have no piece
     const int soff = (IDX_VEC ? lrow * RPL : lrow) * LDS + lpiece * 4;
     int pg = 0, pb = 0;
     auto prefetch = [&](int stage) {
@@ -305,8 +311,9 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         } else {
 #pragma unroll
             for (int it = 0; it < RPL; ++it) {
-                const uint32_t row = idx[it * RPI + lrow];
-                cp_async16_if(pact, st + it * RPI * LDS + soff, zb + (size_t)row * ZS);
+                const uint32_t row = idx[it * RPI + lrow];          // (ragged tail: reads the accept words, copy predicated off)
+                const bool p = RAGGED && it == RPL - 1 ? (pact && it * RPI + lrow < 64) : pact;
+                cp_async16_if(p, st + it * RPI * LDS + soff, zb + (size_t)row * ZS);
             }
         }
         if (!FULL) { if (++pb == nb) { pb = 0; ++pg; } } else { ++pg; }

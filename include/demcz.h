@@ -52,8 +52,11 @@ enum { DEMCZ_SYNC_STRICT = 0, DEMCZ_SYNC_OVERLAP = 1 };
  *   IN_PLACE: stored straight into the peers' slots (no second pass; best while the push hides under compute),
  *   PACKED  : stored densely into a staging ring next to each peer's archive (up to 1.6x fewer lines on the links)
  *             and scattered into the slots by the receiver before the segment becomes drawable,
- *   AUTO    : PACKED when slots have padding and world > 4, else IN_PLACE.  Results are identical either way. */
-enum { DEMCZ_XCHG_AUTO = 0, DEMCZ_XCHG_IN_PLACE = 1, DEMCZ_XCHG_PACKED = 2 };
+ *   DENSE_SLOTS: no padding at all — the archive keeps rows back to back (slot = 4*ceil(d/4) floats), so the in-place
+ *             push is already dense and nothing is scattered; the gather pays for rows that straddle a line instead
+ *             (1.39x the DRAM bytes per row at d = 20).  Fixed at demcz_create (it is the archive layout),
+ *   AUTO    : DENSE_SLOTS when world > 4, else IN_PLACE.  Results are identical in every layout. */
+enum { DEMCZ_XCHG_AUTO = 0, DEMCZ_XCHG_IN_PLACE = 1, DEMCZ_XCHG_PACKED = 2, DEMCZ_XCHG_DENSE_SLOTS = 3 };
 
 /* Mirror of DEMCopt (src/DEMC.jl:24-39) + the keyword arguments of demcz_sample (src/demcz.jl:9)
  * and demcz_anneal (src/demcz_anneal.jl:18), as a POD.  Field meaning == reference option of the

@@ -83,7 +83,7 @@ def test_two_gpus_reproduce_one_gpu_bitwise(sync_mode, p2p):
 @pytest.mark.parametrize("d,sync_mode", [(10, "strict"), (10, "overlap"), (20, "strict"), (20, "overlap"), (13, "overlap")])
 def test_two_gpus_packed_exchange_bitwise(d, sync_mode):
     """DEMCZ_XCHG_PACKED: rows cross NVLink densely through the staging ring and are scattered into their padded
-    slots by the receiver (d = 10: 3 pieces in a 4-piece slot, d = 20: 5 in 8, d = 13: 4 in 4 -> stays in place).
+    slots by the receiver; DEMCZ_XCHG_DENSE_SLOTS: the archive itself has no padding (d = 10: 3 pieces in a 4-piece slot, d = 20: 5 in 8, d = 13: 4 in 4 -> stays in place).
     More K-blocks than the ring is deep, state / archive / accept counts identical to one GPU."""
     N, K, G = 512, 3, 36
     S = 0.3 * np.ones((d, d)) + 0.7 * np.eye(d)
@@ -135,7 +135,7 @@ def test_two_gpus_packed_exchange_bitwise(d, sync_mode):
         assert not err, err
         return out
 
-    for layout in ("packed", "in_place"):
+    for layout in ("packed", "in_place", "dense_slots"):
         out = run2(layout)
         np.testing.assert_array_equal(np.concatenate([o[0] for o in out]), X1)
         np.testing.assert_array_equal(np.concatenate([o[1] for o in out]), lp1)
