@@ -308,12 +308,34 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
     // every rank takes the same decision (same opts); with dense slots (ZS == LD) the in-place push is already packed
     const int lay = c->o.exchange_layout;
     c->xchg_packed = c->ZS != c->LD && lay == DEMCZ_XCHG_PACKED;
+    // overlap mode, rows stored in place: with DEMCZ_FUSED_PUSH=1 the next step-kernel launch carries the push itself
+    // (demcz_step.cuh, PUSH).  Opt-in: measured at parity with the separate kernel on 2 GPUs.
+    const char* env = getenv("DEMCZ_FUSED_PUSH");
+    c->fuse_push = c->o.sync_mode == DEMCZ_SYNC_OVERLAP && !c->xchg_packed && env && atoi(env) == 1;
     return DEMCZ_OK;
 }
 
 // Completes the archive segment starting at physical row `phys_row0` on every rank.  `side`: issue on the side
 // stream with the second communicator (overlap mode), else on the compute stream.
+static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned long long seq);
+
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
+{
+    return exchange_seq(c, phys_row0, side, (unsigned long long)c->appends + 1);       // this is segment number `appends`
+}
+
+int demcz_comm_flush_pending_push(demcz_ctx* c)
+{
+    if (!c->push_pending) return DEMCZ_OK;
+    c->push_pending = false;
+    const bool packed = c->xchg_packed;          // (never both; the stand-alone kernel stores in place)
+    c->xchg_packed = false;
+    int rc = exchange_seq(c, c->push_row0, false, c->push_seq);
+    c->xchg_packed = packed;
+    return rc;
+}
+
+static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned long long seq)
 {
     if (c->o.world == 1) return DEMCZ_OK;
     if (phys_row0 + c->o.N_global > c->zcap)
@@ -332,11 +354,10 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
         const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
         const long long total = (long long)c->o.N * C;
         const int grid = (int)std::min<long long>(32, (total + 255) / 256);      // measured: 16..128 CTAs move the same bytes/s (link-bound)
-        const unsigned long long seq = (unsigned long long)c->appends + 1;       // this is segment number `appends`
         unsigned int* done = (unsigned int*)(c->d_barrier + (side ? 1 : 0));
         mark();
         if (c->xchg_packed) {
-            const int buf = (int)(c->appends % kStageDepth);
+            const int buf = (int)((seq - 1) % kStageDepth);
             const unsigned long long base = demcz_stage_off_floats(c) + ((size_t)buf * c->o.N_global + c->o.chain_offset) * c->LD;
             push_rows_kernel<true><<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C, base,
                                                          demcz_flag_off_floats(c), c->o.rank, seq, done);

@@ -86,6 +86,11 @@ struct demcz_ctx {
     bool peers_open = false;
     int64_t appends = 0;                         // archive appends so far (overlap mode: visibility lags by one)
     int64_t vis_waited = 0;
+    bool step_full = false;                      // the closed-form step launches use the single-full-block kernel
+    bool fuse_push = false;                      // overlap + in-place push: issued from inside the next step-kernel launch
+    bool push_pending = false;                   // a segment is appended locally but not pushed yet (fused push)
+    int64_t push_row0 = 0;                       // its physical first row and
+    unsigned long long push_seq = 0;             // the sequence number its flag words will carry
     bool xchg_packed = false;                    // DEMCZ_XCHG_PACKED in effect: rows travel densely through the staging ring
     int64_t unpacked = 0;                        // packed exchange: segments 0 .. unpacked-1 have been scattered into the slots
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
@@ -113,6 +118,7 @@ int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens);
 
 // demcz_comm.cu — no-ops when world == 1
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);
+int demcz_comm_flush_pending_push(demcz_ctx* c);             // fused push: the segment no later launch will carry (end of a run)
 int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);     // + packed exchange: scatters the landed segments into their slots
 int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n);
 int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);

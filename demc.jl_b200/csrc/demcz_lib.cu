@@ -262,12 +262,12 @@ MvnParams<LD> make_params(const demcz_ctx* c, bool jmajor)
 // resident blocks per SM the register allocation is held to (4 warps per block)
 template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
 
-template <int LD, bool ACC, bool FULL, bool DENSE>
+template <int LD, bool ACC, bool FULL, bool DENSE, bool PUSH = false>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE>;
-    const size_t smem = (size_t)kWarps * 2 * SL::FLOATS * sizeof(float);
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE, PUSH>;
+    const size_t smem = (size_t)kWarps * (2 * SL::FLOATS + (PUSH ? 32 * SL::LDS : 0)) * sizeof(float);   // + the fused push's row stash
     static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
     const int dev = c->device & 63;
     if (!configured[dev]) {
@@ -286,6 +286,8 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 template <int LD, bool DENSE>
 cudaError_t launch_step_lay(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
+    if (full && a.npeers > 0)                   // fused push (full-block launches only; demcz_archive_appended arranges that)
+        return acc ? launch_step_t<LD, true, true, DENSE, true>(c, a) : launch_step_t<LD, false, true, DENSE, true>(c, a);
     if (full) return acc ? launch_step_t<LD, true, true, DENSE>(c, a) : launch_step_t<LD, false, true, DENSE>(c, a);
     return acc ? launch_step_t<LD, true, false, DENSE>(c, a) : launch_step_t<LD, false, false, DENSE>(c, a);
 }
@@ -667,7 +669,15 @@ int demcz_archive_appended(demcz_ctx* c)
     const demcz_opts& o = c->o;
     const int64_t row0 = c->M % c->zcap;
     if (o.world > 1) {
-        if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
+        if (c->fuse_push && c->lik_kind == DEMCZ_LIK_MVN && c->step_full) {
+            // overlap mode, closed-form path: the next step-kernel launch pushes this segment while it computes
+            // (demcz_run flushes it with the stand-alone kernel if no launch follows)
+            if (row0 + o.N_global > c->zcap)
+                return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "multi-GPU append segment wraps the archive ring; make archive_capacity and M0 multiples of N");
+            c->push_pending = true;
+            c->push_row0 = row0;
+            c->push_seq = (unsigned long long)c->appends + 1;
+        } else if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
             const int slot = (int)(c->appends & 1);
             CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
             CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
@@ -878,8 +888,18 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.win_skip_gi = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : -1;
             if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift2, c->shift, sizeof a.shift2); }
 
-            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             const bool full = o.Nblocks == 1 && a.blocks[0].mask == (o.d == 32 ? 0xFFFFFFFFu : ((1u << o.d) - 1u));
+            c->step_full = full;
+            if (c->push_pending && full) {               // this launch carries the exchange of the last appended segment
+                for (int r = 0; r < o.world; ++r) if (r != o.rank) a.peer[a.npeers++] = c->peerZ[r];
+                a.push_row0 = (uint32_t)c->push_row0;
+                a.flag_off_floats = demcz_flag_off_floats(c);
+                a.my_rank = o.rank;
+                a.push_seq = c->push_seq;
+                a.push_done = (unsigned int*)(c->d_barrier + 1);
+                c->push_pending = false;
+            }
+            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             CU(c, launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
@@ -916,6 +936,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         }
     }
     if (o.world > 1 && o.sync_mode == DEMCZ_SYNC_OVERLAP) {                  // drain the exchange: the archive is complete when the call returns
+        rc = demcz_comm_flush_pending_push(c);
+        if (rc != DEMCZ_OK) return rc;
         if (c->appends > 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 1) & 1], 0));
         rc = demcz_comm_wait_segment(c, c->appends);
         if (rc != DEMCZ_OK) return rc;
