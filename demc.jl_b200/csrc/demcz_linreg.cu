@@ -202,32 +202,60 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
         z2 = a.Z + (size_t)r2 * a.ZS;
         a.wacc[chain] = w.z;
     }
+    // Columns in groups of 8 (= one Philox jitter call): every load of a group is issued before its first store, so
+    // the (possibly aliasing) stores serialise groups, not columns — 4 memory round trips for p = 32 instead of 32.
+    // Arithmetic and summation order are those of a plain column loop.
+    const int LD4 = (a.d + 3) & ~3;                 // floats of an archive row that exist (rows are 16-byte aligned)
     double lin = 0.0;
-    float2 zn[4];
-    for (int k = 0; k < a.d; ++k) {
-        const float x = a.X[(size_t)k * a.ldx + chain];
-        float xp = x;
+    for (int k0 = 0; k0 < a.d; k0 += 8) {
+        float x[8], dz[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) x[j] = (k0 + j < a.d) ? a.X[(size_t)(k0 + j) * a.ldx + chain] : 0.f;
+        float2 zn[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
         if (propose) {
-            if ((k & 7) == 0 && a.group_mask(k) != 0) {
-                const u32x4 wn = philox4x32_10(cid, g_lo, ((uint32_t)a.block << 16) | (uint32_t)(1 + (k >> 3)), g_hi, a.keys);
+            const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+            const float4 a0 = *reinterpret_cast<const float4*>(z1 + k0), b0 = *reinterpret_cast<const float4*>(z2 + k0);
+            const float4 a1 = (k0 + 4 < LD4) ? *reinterpret_cast<const float4*>(z1 + k0 + 4) : z;
+            const float4 b1 = (k0 + 4 < LD4) ? *reinterpret_cast<const float4*>(z2 + k0 + 4) : z;
+            dz[0] = a0.x - b0.x; dz[1] = a0.y - b0.y; dz[2] = a0.z - b0.z; dz[3] = a0.w - b0.w;
+            dz[4] = a1.x - b1.x; dz[5] = a1.y - b1.y; dz[6] = a1.z - b1.z; dz[7] = a1.w - b1.w;
+            if (a.group_mask(k0) != 0) {
+                const u32x4 wn = philox4x32_10(cid, g_lo, ((uint32_t)a.block << 16) | (uint32_t)(1 + (k0 >> 3)), g_hi, a.keys);
                 zn[0] = box_muller16(wn.x); zn[1] = box_muller16(wn.y); zn[2] = box_muller16(wn.z); zn[3] = box_muller16(wn.w);
             }
-            if (a.in_block(k)) {
-                const float2 zz = zn[(k & 7) >> 1];
-                const float z = (k & 1) ? zz.y : zz.x;
-                xp = fmaf(a.cscale, z1[k] - z2[k], fmaf(a.eps[k], z, x));
-            }
-            a.Xprop[(size_t)k * a.ldx + chain] = xp;
-            if (a.tr_xprop) a.tr_xprop[(((size_t)(a.grel - 1) * a.nblocks + a.block) * a.d + k) * a.N + chain] = xp;
         }
-        const double dd = (double)xp - a.b0[k];
-        const float df = (float)dd;
-        const float hi = tc::to_tf32(df);
-        const float lo = tc::to_tf32(df - hi);
-        a.Dhi[(size_t)chain * a.ppad + k] = hi;
-        a.Dlo[(size_t)chain * a.ppad + k] = lo;
-        // the GEMM sees hi + lo; use the same value in the linear term
-        lin += ((double)hi + (double)lo) * a.g[k];
+        float hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int k = k0 + j;
+            float xp = x[j];
+            if (propose && k < a.d && a.in_block(k)) {
+                const float2 zz = zn[j >> 1];
+                xp = fmaf(a.cscale, dz[j], fmaf(a.eps[k], (j & 1) ? zz.y : zz.x, x[j]));
+            }
+            x[j] = xp;
+            const double dd = (double)xp - (k < a.d ? a.b0[k] : 0.0);
+            const float df = (float)dd;
+            hi[j] = k < a.d ? tc::to_tf32(df) : 0.f;
+            lo[j] = k < a.d ? tc::to_tf32(df - hi[j]) : 0.f;
+            // the GEMM sees hi + lo; use the same value in the linear term
+            if (k < a.d) lin += ((double)hi[j] + (double)lo[j]) * a.g[k];
+        }
+        if (propose) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int k = k0 + j;
+                if (k < a.d) {
+                    a.Xprop[(size_t)k * a.ldx + chain] = x[j];
+                    if (a.tr_xprop) a.tr_xprop[(((size_t)(a.grel - 1) * a.nblocks + a.block) * a.d + k) * a.N + chain] = x[j];
+                }
+            }
+        }
+        // operand rows are ppad (32 or 64) floats and zero beyond d: whole 16-byte stores
+        float4* dh = reinterpret_cast<float4*>(a.Dhi + (size_t)chain * a.ppad + k0);
+        float4* dl = reinterpret_cast<float4*>(a.Dlo + (size_t)chain * a.ppad + k0);
+        dh[0] = make_float4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
+        dl[0] = make_float4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
     }
     a.lin[chain] = lin;
 }
@@ -261,7 +289,13 @@ __global__ void linreg_accept_kernel(const AccArgs a)
     int acc_i = 0, win_i = 0;
     if (active) {
         double q = 0.0;
-        for (int r = 0; r < a.R; ++r) q += a.partial[(size_t)r * a.Npad + chain];
+        for (int r0 = 0; r0 < a.R; r0 += 16) {               // 16 loads in flight, summed in the fixed order r = 0, 1, ...
+            double pr[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) pr[j] = (r0 + j < a.R) ? a.partial[(size_t)(r0 + j) * a.Npad + chain] : 0.0;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (r0 + j < a.R) q += pr[j];
+        }
         const double lpp = -0.5 * (a.ssr0 - 2.0 * a.lin[chain] + q);
         const double lp = a.lp[chain];
         if (a.block == 0 && a.lp_gen0) a.lp_gen0[chain] = lp;
@@ -275,7 +309,13 @@ __global__ void linreg_accept_kernel(const AccArgs a)
         }
         double lpn = lp;
         if (acc) {
-            for (int k = 0; k < a.d; ++k) a.X[(size_t)k * a.ldx + chain] = a.Xprop[(size_t)k * a.ldx + chain];
+            for (int k0 = 0; k0 < a.d; k0 += 8) {             // loads of a group before its stores (see linreg_prepare_kernel)
+                float t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (k0 + j < a.d) t[j] = a.Xprop[(size_t)(k0 + j) * a.ldx + chain];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) if (k0 + j < a.d) a.X[(size_t)(k0 + j) * a.ldx + chain] = t[j];
+            }
             a.lp[chain] = lpp;
             lpn = lpp;
             acc_i = 1;
@@ -284,26 +324,46 @@ __global__ void linreg_accept_kernel(const AccArgs a)
             const bool changed = lpn != (a.lp_gen0 ? a.lp_gen0[chain] : lp);
             if (changed && a.count_run) a.chain_changed[chain] += 1;
             win_i = (changed && a.count_win) ? 1 : 0;
-            if (a.hist) {
-                for (int k = 0; k < a.d; ++k) a.hist[((size_t)(a.grel - 1) * a.d + k) * a.N + chain] = a.X[(size_t)k * a.ldx + chain];
-                a.lphist[(size_t)(a.grel - 1) * a.N + chain] = lpn;
-            }
-            if (a.Zw) {
+            if (a.hist || a.Zw) {
                 uint32_t row = a.append_row0 + a.chain_offset + (uint32_t)chain;
                 if (row >= a.zcap) row -= a.zcap;
-                for (int k = 0; k < a.d; ++k) a.Zw[(size_t)row * a.ZS + k] = a.X[(size_t)k * a.ldx + chain];
+                const int LD4 = (a.d + 3) & ~3;
+                for (int k0 = 0; k0 < a.d; k0 += 8) {
+                    float t[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) t[j] = (k0 + j < a.d) ? a.X[(size_t)(k0 + j) * a.ldx + chain] : 0.f;
+                    if (a.hist) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            if (k0 + j < a.d) a.hist[((size_t)(a.grel - 1) * a.d + k0 + j) * a.N + chain] = t[j];
+                    }
+                    if (a.Zw) {                                // rows are 16-byte aligned; the padding up to 4*ceil(d/4) is written as zeros
+                        float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * a.ZS + k0);
+                        dst[0] = make_float4(t[0], t[1], t[2], t[3]);
+                        if (k0 + 4 < LD4) dst[1] = make_float4(t[4], t[5], t[6], t[7]);
+                    }
+                }
+                if (a.hist) a.lphist[(size_t)(a.grel - 1) * a.N + chain] = lpn;
             }
         }
     }
     if (a.last_block && a.S1) {                         // split-Rhat accumulators (src/utils.jl:2-20)
-        for (int k = 0; k < a.d; ++k) {
-            float t = 0.f;
-            if (active) {
-                t = a.X[(size_t)k * a.ldx + chain] - a.shift[k];
-                a.S1[(size_t)k * a.ldx + chain] += t;
+        for (int k0 = 0; k0 < a.d; k0 += 8) {
+            float t[8], s1[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const bool on = active && k0 + j < a.d;
+                t[j] = on ? a.X[(size_t)(k0 + j) * a.ldx + chain] - a.shift[k0 + j] : 0.f;
+                s1[j] = on ? a.S1[(size_t)(k0 + j) * a.ldx + chain] : 0.f;
             }
-            const double v = warp_sum((double)t * (double)t);
-            if ((threadIdx.x & 31) == 0) atomicAdd(&red_s2[k], v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (k0 + j < a.d) {                            // warp-uniform
+                    if (active) a.S1[(size_t)(k0 + j) * a.ldx + chain] = s1[j] + t[j];
+                    const double v = warp_sum((double)t[j] * (double)t[j]);
+                    if ((threadIdx.x & 31) == 0) atomicAdd(&red_s2[k0 + j], v);
+                }
+            }
         }
     }
     const int wa = warp_sum(acc_i), ww = warp_sum(win_i);
