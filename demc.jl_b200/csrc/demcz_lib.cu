@@ -279,8 +279,17 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     const int threads = kWarps * 32;
     const int grid = (a.N + threads - 1) / threads;
     const MvnParams<LD> P = make_params<LD>(c, kStepOpt & OPT_JMAJOR);
-    kern<<<grid, threads, smem, c->stream>>>(a, P);
-    return cudaGetLastError();
+    // Programmatic dependent launch: consecutive step launches of a stream overlap the next launch's scheduling and
+    // prologue with this one's tail; the kernel waits (griddepcontrol.wait) before it touches anything a predecessor wrote.
+    static const bool pdl = !(getenv("DEMCZ_PDL") && atoi(getenv("DEMCZ_PDL")) == 0);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, a, P);
 }
 
 template <int LD, bool DENSE>

@@ -260,6 +260,11 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     const int cl = active ? chain : a.N - 1;          // clamped: idle lanes shadow the last chain, never store
     const uint32_t cid = a.chain_offset + (uint32_t)cl;
 
+    // programmatic dependent launch (no-ops without the launch attribute): let the next launch of the stream be
+    // scheduled as soon as every CTA of this one is resident; wait here for the predecessor's writes (state, appended
+    // rows, counters) — nothing written by a kernel is read or overwritten above this line
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
     if (PUSH && threadIdx.x < 7) s_peer[threadIdx.x] = a.peer[threadIdx.x];
     if (threadIdx.x < 2) red_cnt[threadIdx.x] = 0u;
     if (ACC && threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
