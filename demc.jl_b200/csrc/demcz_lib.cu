@@ -5,8 +5,7 @@
 //   Rhat_gelman    src/utils.jl:2-20
 // No CPU fallback: every compute entry point needs a CUDA device.
 #include "../../include/demcz.h"
-#include "demcz_step.cuh"
-#include "demcz_internal.h"
+#include "demcz_step_host.h"
 
 #include <cmath>
 #include <cstdarg>
@@ -229,106 +228,14 @@ __global__ void rhat_partial_kernel(const float* __restrict__ S1h0, const float*
 }  // namespace
 
 // ------------------------------------------------------------------------------------------------
-// kernel dispatch
+// kernel dispatch (the step-kernel instantiations live in demcz_step_launch.cu, compiled once per width group)
 // ------------------------------------------------------------------------------------------------
 namespace {
-
-constexpr int kWarps = 4;
-
-// production structure of the step kernel (see tools/step_tune.cu and profiles/ for how it was chosen)
-constexpr int kStepOpt = DEMCZ_STEP_OPT;
-
-template <int LD>
-MvnParams<LD> make_params(const demcz_ctx* c, bool jmajor)
-{
-    using MP = MvnParams<LD>;
-    MvnParams<LD> P;
-    memset(&P, 0, sizeof P);
-    const int d = c->o.d;
-    auto W = [&](int i, int j) { return (i < d && j < d && j <= i) ? c->mvn_W[(size_t)i * d + j] : 0.f; };
-    for (int k = 0; k < LD / 2; ++k)
-        P.mu2[k] = make_float2(2 * k < d ? c->mvn_mu[2 * k] : 0.f, 2 * k + 1 < d ? c->mvn_mu[2 * k + 1] : 0.f);
-    if (jmajor) {
-        for (int j = 0; j < LD; ++j)
-            for (int i2 = j / 2; i2 < LD / 2; ++i2) P.W[MP::wj_off(j) + i2 - j / 2] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
-    } else {
-        for (int i2 = 0; i2 < LD / 2; ++i2)
-            for (int j = 0; j < 2 * i2 + 2; ++j) P.W[i2 * (i2 + 1) + j] = make_float2(W(2 * i2, j), W(2 * i2 + 1, j));
-    }
-    P.c0 = c->mvn_c0;
-    return P;
-}
-
-// resident blocks per SM the register allocation is held to (4 warps per block)
-template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
-
-template <int LD, bool ACC, bool FULL, bool DENSE, bool PUSH = false>
-cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
-{
-    using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE, PUSH>;
-    const size_t smem = (size_t)kWarps * (2 * SL::FLOATS + (PUSH ? 32 * SL::LDS : 0)) * sizeof(float);   // + the fused push's row stash
-    static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
-    const int dev = c->device & 63;
-    if (!configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        configured[dev] = true;
-    }
-    const int threads = kWarps * 32;
-    const int grid = (a.N + threads - 1) / threads;
-    const MvnParams<LD> P = make_params<LD>(c, kStepOpt & OPT_JMAJOR);
-    // Programmatic dependent launch: consecutive step launches of a stream overlap the next launch's scheduling and
-    // prologue with this one's tail; the kernel waits (griddepcontrol.wait) before it touches anything a predecessor wrote.
-    static const bool pdl = !(getenv("DEMCZ_PDL") && atoi(getenv("DEMCZ_PDL")) == 0);
-    cudaLaunchConfig_t cfg;
-    memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, kern, a, P);
-}
-
-template <int LD, bool DENSE>
-cudaError_t launch_step_lay(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    if (full && a.npeers > 0)                   // fused push (full-block launches only; demcz_archive_appended arranges that)
-        return acc ? launch_step_t<LD, true, true, DENSE, true>(c, a) : launch_step_t<LD, false, true, DENSE, true>(c, a);
-    if (full) return acc ? launch_step_t<LD, true, true, DENSE>(c, a) : launch_step_t<LD, false, true, DENSE>(c, a);
-    return acc ? launch_step_t<LD, true, false, DENSE>(c, a) : launch_step_t<LD, false, false, DENSE>(c, a);
-}
-
-template <int LD>
-cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    if constexpr (zslot(LD) != LD) {            // dense slots (DEMCZ_XCHG_DENSE_SLOTS) only differ where the slot has padding
-        if (c->ZS == LD) return launch_step_lay<LD, true>(c, a, acc, full);
-    }
-    return launch_step_lay<LD, false>(c, a, acc, full);
-}
-
-cudaError_t launch_step(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    switch (c->LD) {
-        case 4:  return launch_step_ld<4>(c, a, acc, full);
-        case 8:  return launch_step_ld<8>(c, a, acc, full);
-        case 12: return launch_step_ld<12>(c, a, acc, full);
-        case 16: return launch_step_ld<16>(c, a, acc, full);
-        case 20: return launch_step_ld<20>(c, a, acc, full);
-        case 24: return launch_step_ld<24>(c, a, acc, full);
-        case 28: return launch_step_ld<28>(c, a, acc, full);
-        case 32: return launch_step_ld<32>(c, a, acc, full);
-    }
-    return cudaErrorInvalidValue;
-}
 
 template <int LD>
 cudaError_t launch_eval_t(demcz_ctx* c, const float* X, int n, int ldx, float* out)
 {
-    const MvnParams<LD> P = make_params<LD>(c, false);
+    const MvnParams<LD> P = demcz_make_mvn_params<LD>(c, false);
     mvn_eval_kernel<LD><<<(n + 127) / 128, 128, 0, c->stream>>>(X, n, ldx, c->o.d, out, P);
     return cudaGetLastError();
 }
@@ -909,7 +816,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
                 c->push_pending = false;
             }
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
-            CU(c, launch_step(c, a, acc, full));
+            CU(c, demcz_launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
             rc = demcz_hist_end(c, g, n_gens);
