@@ -98,3 +98,51 @@ def test_host_diagnostics_match_oracle():
     lo = rng.integers(0, 3, size=(6, 41)).astype(float)
     ar, rh = DEMC.convergence_check(chain, lo, verbose=False)
     np.testing.assert_array_equal(ar, orc.accept_ratio(lo))
+
+
+def test_header_is_plain_c_and_struct_layout_matches_ctypes(tmp_path):
+    """include/demcz.h must be consumable by a C compiler (the Julia ccall / cgo style binding sees a C ABI), and the
+    ctypes mirror must agree with the compiler on every field offset of demcz_opts / demcz_run_info."""
+    import subprocess
+    fields_o = [n for n, _ in _lib.Opts._fields_]
+    fields_i = [n for n, _ in _lib.RunInfo._fields_]
+    src = ['#include <stdio.h>', '#include <stddef.h>', '#include "demcz.h"', 'int main(void) {',
+           '  printf("%zu %zu\\n", sizeof(demcz_opts), sizeof(demcz_run_info));']
+    src += [f'  printf("o {f} %zu\\n", offsetof(demcz_opts, {f}));' for f in fields_o]
+    src += [f'  printf("i {f} %zu\\n", offsetof(demcz_run_info, {f}));' for f in fields_i]
+    src += ['  return (int)(DEMCZ_XCHG_DENSE_SLOTS + DEMCZ_SYNC_OVERLAP + DEMCZ_ERR_UNSUPPORTED) * 0;', '}']
+    cfile = tmp_path / "abi.c"
+    cfile.write_text("\n".join(src))
+    exe = tmp_path / "abi"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(cfile)],
+                   check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split("\n")
+    so, si = map(int, out[0].split())
+    assert so == C.sizeof(_lib.Opts) and si == C.sizeof(_lib.RunInfo)
+    for line in out[1:]:
+        if not line:
+            continue
+        which, name, off = line.split()
+        cls = _lib.Opts if which == "o" else _lib.RunInfo
+        assert getattr(cls, name).offset == int(off), (which, name)
+
+
+def test_create_rejects_unknown_exchange_layout():
+    lib = _lib.load()
+    bp = np.array([0, 2], dtype=np.int32)
+    bi = np.array([0, 1], dtype=np.int32)
+    eps = np.ones(2)
+    o = _lib.Opts()
+    o.struct_size = C.sizeof(_lib.Opts)
+    o.N, o.K, o.Ngeneration, o.Nblocks, o.d = 4, 10, 10, 1, 2
+    o.block_ptr = bp.ctypes.data_as(C.POINTER(C.c_int32))
+    o.block_idx = bi.ctypes.data_as(C.POINTER(C.c_int32))
+    o.eps_scale = eps.ctypes.data_as(C.POINTER(C.c_double))
+    o.rank, o.world, o.N_global = 0, 1, 4
+    o.exchange_layout = 9
+    ctx = C.c_void_p()
+    assert lib.demcz_create(C.byref(ctx), C.byref(o), 0) == -1
+    assert b"exchange_layout" in lib.demcz_last_error(None)
+    with pytest.raises(KeyError):
+        DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(2), np.eye(2)), 2, N=4, K=10, Ngeneration=10, blockindex=[[0, 1]],
+                     eps_scale=np.ones(2), γ=2.38, exchange_layout="bogus")
