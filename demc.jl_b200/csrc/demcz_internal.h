@@ -100,13 +100,16 @@ struct demcz_ctx {
 };
 
 // One device allocation holds the archive and everything the peers write into, so that a single IPC handle maps it:
-//   [zcap row slots][8 x u64 segment flags, 256 B][staging ring: kStageDepth x N_global dense rows of LD floats]   (ring: world > 1)
+//   [zcap row slots][8 x u64 segment flags, 256 B][staging ring: kStageDepth x N_global dense rows of LD floats]   (ring: packed layout)
 // Depth 4: a sender refills buffer s % 4 with segment s + 4 only after its K-block s + 4 started, which needed the
 // receiver's segment s + 2, which the receiver pushes after its K-block s + 2, which started after it unpacked segment s.
 constexpr int kStageDepth = 4;
 inline size_t demcz_flag_off_floats(const demcz_ctx* c) { return (size_t)c->zcap * c->ZS; }
 inline size_t demcz_stage_off_floats(const demcz_ctx* c) { return (demcz_flag_off_floats(c) + 64 + 31) / 32 * 32; }
-inline size_t demcz_stage_floats(const demcz_ctx* c) { return c->o.world > 1 ? (size_t)kStageDepth * c->o.N_global * c->LD : 0; }
+inline size_t demcz_stage_floats(const demcz_ctx* c)     // only the packed layout has a staging ring
+{
+    return (c->o.world > 1 && c->o.exchange_layout == DEMCZ_XCHG_PACKED) ? (size_t)kStageDepth * c->o.N_global * c->LD : 0;
+}
 
 int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
 int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart);
