@@ -6,7 +6,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ["Rhat_gelman", "flatten_chain", "mean_cov_chain", "convergence_check"]
+__all__ = ["Rhat_gelman", "flatten_chain", "mean_cov_chain", "convergence_check", "extract_best"]
 
 
 def Rhat_gelman(chain, Npop=None, Ngeneration=None, Npar=None):
@@ -57,3 +57,14 @@ def convergence_check(chain, log_obj, figure_path=None, *, verbose=True, parname
         print(accept_ratio)
         print(f"\nRhat Gelman: {Rhat}\n")
     return accept_ratio, Rhat
+
+
+def extract_best(mc):
+    """(best log-objective, its parameter vector) over the whole history — what src/utils.jl:120-125 intends (the
+    upstream body uses `findn`, gone since Julia 1.0); first maximum in column-major order like Julia's `findn`."""
+    lo = np.asarray(mc.log_obj)
+    if lo.size == 0:
+        raise ValueError("extract_best: the MC record holds no history (store_chain was off)")
+    flat = int(np.argmax(lo.ravel(order="F")))            # NaN-free by construction: a NaN proposal is never accepted
+    row, col = flat % lo.shape[0], flat // lo.shape[0]
+    return float(lo[row, col]), np.array(mc.chain[row, :, col], dtype=np.float64)

@@ -146,3 +146,14 @@ def test_create_rejects_unknown_exchange_layout():
     with pytest.raises(KeyError):
         DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(2), np.eye(2)), 2, N=4, K=10, Ngeneration=10, blockindex=[[0, 1]],
                      eps_scale=np.ones(2), γ=2.38, exchange_layout="bogus")
+
+
+def test_extract_best_returns_first_maximum_of_the_history():
+    rng = np.random.default_rng(3)
+    chain = rng.normal(size=(5, 3, 7))
+    lo = rng.normal(size=(5, 7))
+    lo[2, 4] = lo[4, 1] = 10.0                       # a tie: column-major order picks generation 1 (chain 4) first
+    mc = DEMC.MC(chain, lo, chain[:, :, -1], lo[:, -1])
+    val, par = DEMC.extract_best(mc)
+    assert val == 10.0
+    np.testing.assert_array_equal(par, chain[4, :, 1])
