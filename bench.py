@@ -262,6 +262,9 @@ def main():
         gps = args.gens_per_step or (10 if w["kind"] == "linreg" else 100)
         return w, gps, _cfg(w, gps)
 
+    # what DEMCZ_XCHG_AUTO resolves to (include/demcz.h): rows without slot padding above 4 GPUs
+    eff_layout = args.exchange_layout if args.exchange_layout != "auto" else ("dense_slots (auto)" if world > 4 else "in_place (auto)")
+
     def _cfg(w, gps):
         K = w["K"]
         return dict(workload=w["name"], chains_per_gpu=w["chains_per_gpu"], chains_total=w["chains_per_gpu"] * max(world, 1),
@@ -273,7 +276,7 @@ def main():
                    else "archive > L2 (126 MB): random gathers miss L2; no flush needed"),
                sync_mode=args.sync,
                parallelism=(f"chains sharded x{world}; appended rows exchanged every K generations by "
-                            + (f"our push kernel into peer-mapped archive replicas (NVLink; layout {args.exchange_layout}), published by flag words" if args.exchange == "p2p" else "ncclAllGather")
+                            + (f"our push kernel into peer-mapped archive replicas (NVLink; archive layout {eff_layout}), published by flag words" if args.exchange == "p2p" else "ncclAllGather")
                             + (", on a side stream under the next K-block" if args.sync == "overlap" else ", on the compute stream")))
 
     # ---------------------------------------------------------------- reference arm (CPU) -------
