@@ -157,3 +157,31 @@ def test_extract_best_returns_first_maximum_of_the_history():
     val, par = DEMC.extract_best(mc)
     assert val == 10.0
     np.testing.assert_array_equal(par, chain[4, :, 1])
+
+
+def test_julia_shim_structs_match_the_abi_field_for_field():
+    """The Julia shim is written without a Julia toolchain in the image, so its `COpts` / `CRunInfo` mirrors are held to
+    the ctypes mirror (itself held to the C header by the offset test above): same field names, order and C types."""
+    src = open(os.path.join(ROOT, "demc.jl_b200", "julia", "DEMC.jl")).read()
+    jl2c = {"Int32": C.c_int32, "Int64": C.c_int64, "UInt64": C.c_uint64, "Float64": C.c_double,
+            "Ptr{Int32}": C.POINTER(C.c_int32), "Ptr{Float64}": C.POINTER(C.c_double)}
+
+    def fields(name):
+        body = re.search(r"struct %s\n(.*?)\nend" % name, src, flags=re.S).group(1)
+        out = []
+        for part in re.split(r"[;\n]", body):
+            part = part.split("#")[0].strip()
+            if part:
+                n, t = part.split("::")
+                out.append((n.strip(), jl2c[t.strip()]))
+        return out
+
+    for jl_name, cls in (("COpts", _lib.Opts), ("CRunInfo", _lib.RunInfo)):
+        jl = fields(jl_name)
+        py = list(cls._fields_)
+        assert [n for n, _ in jl] == [n for n, _ in py], jl_name
+        for (n, tj), (_, tp) in zip(jl, py):
+            assert C.sizeof(tj) == C.sizeof(tp) and (tj is tp or "LP_" in tp.__name__), (jl_name, n)
+    # every ccall names a function the header declares
+    called = set(re.findall(r"ccall\(\(:(demcz_[a-z0-9_]+)", src))
+    assert called and called <= set(_header_functions())
