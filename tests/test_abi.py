@@ -185,3 +185,19 @@ def test_julia_shim_structs_match_the_abi_field_for_field():
     # every ccall names a function the header declares
     called = set(re.findall(r"ccall\(\(:(demcz_[a-z0-9_]+)", src))
     assert called and called <= set(_header_functions())
+
+
+def test_julia_ccall_signatures_have_the_arity_of_the_c_prototypes():
+    hdr = open(os.path.join(ROOT, "include", "demcz.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    proto = {}
+    for m in re.finditer(r"\b(demcz_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", hdr):
+        args = m.group(2).strip()
+        proto[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    src = open(os.path.join(ROOT, "demc.jl_b200", "julia", "DEMC.jl")).read()
+    seen = 0
+    for m in re.finditer(r"ccall\(\(:(demcz_[a-z0-9_]+),\s*\w+\),\s*\w+,\s*\(([^)]*)\)", src):
+        name, types = m.group(1), [t for t in m.group(2).split(",") if t.strip()]
+        assert len(types) == proto[name], (name, types, proto[name])
+        seen += 1
+    assert seen >= 10
