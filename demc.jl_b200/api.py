@@ -146,7 +146,8 @@ class Sampler:
                  autostop=False, autostop_every=1000, autostop_Rhat=1.05, adapt=False, min_gamma=0.1, max_gamma=4.0,
                  adapt_every=500, seed=31953150, gen_offset=0, store_chain=True, init_mode="last_N_of_Z",
                  archive_capacity=0, trace=False, profile=False, device=0, rank=0, world=1, N_global=None,
-                 chain_offset=0, sync_mode="strict", exchange_layout="auto"):
+                 chain_offset=0, sync_mode="strict", exchange_layout="auto", push_engine="auto", thin=1, moments=False,
+                 persistent="auto", snooker_prob=0.0, snooker_gamma=0.0):
         _check_likelihood(logobj)
         self.lib = _lib.load()
         self.d, self.N = int(d), int(N)
@@ -175,7 +176,14 @@ class Sampler:
         o.N_global = self.N if N_global is None else int(N_global)
         o.chain_offset = int(chain_offset)
         o.sync_mode = {"strict": 0, "overlap": 1}[sync_mode]
-        o.exchange_layout = {"auto": 0, "in_place": 1, "packed": 2, "dense_slots": 3}[exchange_layout]
+        if exchange_layout not in ("auto", "in_place", "dense_slots"):
+            raise ValueError(f"exchange_layout must be auto, in_place or dense_slots (got {exchange_layout!r})")
+        o.exchange_layout = {"auto": 0, "in_place": 1, "dense_slots": 3}[exchange_layout]
+        o.push_engine = {"auto": 0, "kernel": 1, "copy_engine": 2}[push_engine]
+        o.thin, o.moments = int(thin), int(bool(moments))
+        o.persistent = {"auto": -1, True: 1, False: 0, 1: 1, 0: 0, -1: -1}[persistent]
+        o.snooker_prob, o.snooker_gamma = float(snooker_prob), float(snooker_gamma)
+        self.thin = max(int(thin), 1)
         self.opts = o
         self.Nblocks = len(blocks)
         self.ctx = C.c_void_p()
@@ -249,7 +257,7 @@ class Sampler:
 
     # -- outputs -----------------------------------------------------------------------------
     def get_chain(self):
-        G = self.generations_total
+        G = self.generations_total // self.thin            # stored generations (opts.thin)
         chain = np.zeros((self.N, self.d, G), order="F")
         log_obj = np.zeros((self.N, G), order="F")
         if G:
@@ -281,6 +289,25 @@ class Sampler:
         cov = np.zeros((self.d, self.d))
         self._check(self.lib.demcz_get_archive_moments(self.ctx, int(first_row), int(n_rows), _dp(mean), _dp(cov)))
         return mean, cov
+
+    def get_history_moments(self, reset=False):
+        """(mean, cov, n) over every generation of every chain so far — mean_cov_chain (src/utils.jl:96-106) of the full
+        history from the device accumulators (needs moments=True)."""
+        mean = np.zeros(self.d)
+        cov = np.zeros((self.d, self.d), order="F")
+        n = C.c_int64()
+        self._check(self.lib.demcz_get_history_moments(self.ctx, _dp(mean), _dp(cov), C.byref(n), int(bool(reset))))
+        return mean, cov, n.value
+
+    def get_archive_checksum(self, first_row=0, n_rows=None):
+        """64-bit checksum of archive rows (equal on every rank of a sharded run iff the replicas are identical)."""
+        if n_rows is None:
+            M = C.c_int64()
+            self._check(self.lib.demcz_get_archive(self.ctx, None, C.byref(M)))
+            n_rows = M.value - first_row
+        h = C.c_uint64()
+        self._check(self.lib.demcz_get_archive_checksum(self.ctx, int(first_row), int(n_rows), C.byref(h)))
+        return h.value
 
     def get_rhat(self):
         r = np.zeros(self.d)
@@ -335,7 +362,8 @@ def _concat_prev(prevrun: Optional[MC], mc: MC) -> MC:
 
 
 def _run(logobj, Zmat, v, *, anneal, prevrun, verbose, print_step, autostop, autostop_Rhat, autostop_every,
-         temperaturefun, T0, TN, adaptγ, seed, device, store_chain, init_mode, archive_capacity, trace, profile):
+         temperaturefun, T0, TN, adaptγ, seed, device, store_chain, init_mode, archive_capacity, trace, profile,
+         thin=1, moments=False, snooker_prob=0.0, snooker_gamma=0.0, persistent="auto", sharded=False, sync_mode="strict"):
     _check_likelihood(logobj)
     Zmat = np.asfortranarray(Zmat, dtype=np.float64)
     d = Zmat.shape[1]
@@ -343,19 +371,38 @@ def _run(logobj, Zmat, v, *, anneal, prevrun, verbose, print_step, autostop, aut
         raise ValueError("Nblocks != length(blockindex)")
     gen_offset = prevrun.generations_total if prevrun is not None else 0
     adaptγ = adaptγ or {}
-    s = Sampler(logobj, d, N=v["N"], K=v["K"], Ngeneration=v["Ngeneration"], blockindex=v["blockindex"],
-                eps_scale=v["eps_scale"], γ=v["γ"], anneal=anneal, T0=T0, TN=TN,
-                autostop=(str(autostop).lstrip(":") == "Rhat") and not anneal, autostop_every=autostop_every,
-                autostop_Rhat=autostop_Rhat, adapt=bool(adaptγ.get("adapt", False)) and anneal,
-                min_gamma=adaptγ.get("minγ", adaptγ.get("min_gamma", 0.1)),
-                max_gamma=adaptγ.get("maxγ", adaptγ.get("max_gamma", 4.0)), adapt_every=adaptγ.get("adapt_every", 500),
-                seed=seed, gen_offset=gen_offset, store_chain=store_chain, init_mode=init_mode,
-                archive_capacity=archive_capacity, trace=trace, profile=profile, device=device)
+    kw = dict(K=v["K"], Ngeneration=v["Ngeneration"], blockindex=v["blockindex"],
+              eps_scale=v["eps_scale"], γ=v["γ"], anneal=anneal, T0=T0, TN=TN,
+              autostop=(str(autostop).lstrip(":") == "Rhat") and not anneal, autostop_every=autostop_every,
+              autostop_Rhat=autostop_Rhat, adapt=bool(adaptγ.get("adapt", False)) and anneal,
+              min_gamma=adaptγ.get("minγ", adaptγ.get("min_gamma", 0.1)),
+              max_gamma=adaptγ.get("maxγ", adaptγ.get("max_gamma", 4.0)), adapt_every=adaptγ.get("adapt_every", 500),
+              seed=seed, gen_offset=gen_offset, store_chain=store_chain, init_mode=init_mode,
+              archive_capacity=archive_capacity, trace=trace, profile=profile, thin=thin, moments=moments,
+              snooker_prob=snooker_prob, snooker_gamma=snooker_gamma, persistent=persistent, sync_mode=sync_mode)
+    from . import dist as _dist
+    rank, world, local_rank = _dist.env_rank_world() if sharded else (0, 1, 0)
+    if world > 1:
+        # the multi-GPU runner (one process per GPU under torchrun): chains sharded contiguously, archive replicated,
+        # appended rows exchanged every K generations — the sync mode of demcz_sample_par (src/demcz.jl:129-137)
+        _dist.ensure_process_group(local_rank)
+        N_global = int(v["N"])
+        n_loc, off = _dist.shard(N_global, rank, world)
+        cap = archive_capacity
+        if cap == 0:                                      # segments must not straddle the ring end: pad M0 up to a multiple of N
+            Zmat, cap = _dist.pad_archive_for_sharding(Zmat, N_global, v["Ngeneration"], v["K"])
+            kw["archive_capacity"] = cap
+        s = _dist.make_sharded_sampler(logobj, d, N_global=N_global, rank=rank, world=world, device=local_rank, **kw)
+    else:
+        n_loc, off = int(v["N"]), 0
+        s = Sampler(logobj, d, N=v["N"], device=device, **kw)
     try:
         s.set_archive(Zmat)
+        if world > 1:
+            _dist.open_peer_archives(s, rank=rank, world=world, device=local_rank)
         if prevrun is not None:
             # X = prevrun.chain[:,:,end]; log_objcurrent = prevrun.log_objcurrent   (src/demcz.jl:20-21)
-            s.set_state(prevrun.Xcurrent, prevrun.log_objcurrent)
+            s.set_state(prevrun.Xcurrent[off:off + n_loc], prevrun.log_objcurrent[off:off + n_loc])
         if anneal and temperaturefun is not tempbaseline:
             G = v["Ngeneration"]
             s.set_temperature_table([temperaturefun(ig, G, T0, TN) for ig in range(1, G + 1)])
@@ -364,14 +411,15 @@ def _run(logobj, Zmat, v, *, anneal, prevrun, verbose, print_step, autostop, aut
             while s.generations_total < v["Ngeneration"]:
                 info = s.run(print_step)
                 X, lp = s.get_state()
-                print("-----------------------")
-                print(f"iteration {s.generations_total}")
-                if anneal:
-                    print(f"bestval = {lp.max()}")
-                else:
-                    print(f"average par = {X.mean(axis=0)}")
-                    print(f"average val = {lp.mean()}")
-                print("-----------------------")
+                if rank == 0:
+                    print("-----------------------")
+                    print(f"iteration {s.generations_total}")
+                    if anneal:
+                        print(f"bestval = {lp.max()}")
+                    else:
+                        print(f"average par = {X.mean(axis=0)}")
+                        print(f"average val = {lp.mean()}")
+                    print("-----------------------")
                 if info["stopped_by_rhat"]:
                     break
         else:
@@ -380,20 +428,27 @@ def _run(logobj, Zmat, v, *, anneal, prevrun, verbose, print_step, autostop, aut
         if store_chain:
             chain, log_obj = s.get_chain()
         else:
-            chain, log_obj = np.zeros((v["N"], d, 0), order="F"), np.zeros((v["N"], 0), order="F")
+            chain, log_obj = np.zeros((n_loc, d, 0), order="F"), np.zeros((n_loc, 0), order="F")
         info["rhat"] = s.get_rhat() if info.get("rhat_valid") else None
+        if moments:
+            info["history_moments"] = s.get_history_moments()
         if trace:
             info["trace"] = s.get_trace()
         Z = s.get_archive()
+        if world > 1:                                     # every rank returns the whole population, like the reference's master
+            info["accepted"] = int(_dist.allreduce_sum(info["accepted"], local_rank))
+            info["proposals"] = int(_dist.allreduce_sum(info["proposals"], local_rank))
+            X, lp = _dist.allgather_rows(X, local_rank), _dist.allgather_rows(lp, local_rank)
+            chain, log_obj = _dist.allgather_rows(chain, local_rank), _dist.allgather_rows(log_obj, local_rank)
     finally:
         s.close()
-    mc = MC(chain, log_obj, X, lp, s.generations_total, info)
+    mc = MC(np.asfortranarray(chain), np.asfortranarray(log_obj), X, lp, s.generations_total, info)
     return _concat_prev(prevrun, mc), Z
 
 
 def demcz_sample(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=None, autostop=None, autostop_Rhat=None,
                  autostop_every=None, seed=31953150, device=0, store_chain=True, init_mode="last_N_of_Z",
-                 archive_capacity=0, trace=False, profile=False):
+                 archive_capacity=0, trace=False, profile=False, **extra):
     """demcz_sample(logobj, Zmat, opts::DEMCopt; prevrun) — src/demcz.jl:1-3, or the positional form
     demcz_sample(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale, γ; ...) — src/demcz.jl:9.
     Returns (mc::MC, Z) with Z = Z[1:M, :]."""
@@ -412,7 +467,19 @@ def demcz_sample(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=Non
             kw[name] = val
     return _run(logobj, Zmat, v, anneal=False, prevrun=prevrun, temperaturefun=tempbaseline, T0=3.0, TN=1e-3,
                 adaptγ=None, seed=seed, device=device, store_chain=store_chain, init_mode=init_mode,
-                archive_capacity=archive_capacity, trace=trace, profile=profile, **kw)
+                archive_capacity=archive_capacity, trace=trace, profile=profile, **kw, **_extra(extra))
+
+
+_EXTRA = ("thin", "moments", "snooker_prob", "snooker_gamma", "persistent", "sharded", "sync_mode")
+
+
+def _extra(extra):
+    """Keyword extensions that have no counterpart in the reference (history thinning, streaming moments, the snooker
+    update, small-N persistent launches, multi-GPU sharding / sync mode)."""
+    bad = set(extra) - set(_EXTRA)
+    if bad:
+        raise TypeError(f"unexpected keyword argument(s) {sorted(bad)}")
+    return extra
 
 
 _ADAPT_DEFAULT = {"adapt": True, "minγ": 0.1, "maxγ": 4.0, "adapt_every": 500}   # src/demcz_anneal.jl:14
@@ -420,7 +487,7 @@ _ADAPT_DEFAULT = {"adapt": True, "minγ": 0.1, "maxγ": 4.0, "adapt_every": 500}
 
 def demcz_anneal(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=None,
                  temperaturefun: Callable = tempbaseline, T0=None, TN=None, adaptγ=None, seed=31953150, device=0,
-                 store_chain=True, init_mode="last_N_of_Z", archive_capacity=0, trace=False, profile=False):
+                 store_chain=True, init_mode="last_N_of_Z", archive_capacity=0, trace=False, profile=False, **extra):
     """demcz_anneal(logobj, Zmat, opts; prevrun, temperaturefun, adaptγ) — src/demcz_anneal.jl:14-16, or the
     positional form (:18).  The schedule is T0*(TN/T0)^(ig/Ngeneration) as intended."""
     if len(args) == 1 and isinstance(args[0], DEMCopt):
@@ -443,7 +510,7 @@ def demcz_anneal(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=Non
                 temperaturefun=temperaturefun, T0=float(T0), TN=float(TN),
                 adaptγ=dict(_ADAPT_DEFAULT) if adaptγ is None else adaptγ, seed=seed, device=device,
                 store_chain=store_chain, init_mode=init_mode, archive_capacity=archive_capacity, trace=trace,
-                profile=profile, **kw)
+                profile=profile, **kw, **_extra(extra))
 
 
 # ------------------------------------------------------------------------------------------------
@@ -451,13 +518,17 @@ def demcz_anneal(logobj, Zmat, *args, prevrun=None, verbose=None, print_step=Non
 # ------------------------------------------------------------------------------------------------
 def demcz_sample_par(logobj, Zmat, *args, sync_every=1000, prevrun=None, workerpool=None, autostop=None, autostop_Rhat=None,
                      verbose=None, **kw):
-    """demcz_sample_par(logobj, Zmat, opts | N, K, ...; sync_every, prevrun, autostop, autostop_Rhat, workerpool).
+    """demcz_sample_par(logobj, Zmat, opts | N, K, ...; sync_every, prevrun, autostop, autostop_Rhat, workerpool)
+    — src/demcz.jl:101-165.
 
-    In the reference one Distributed.jl worker runs each chain for `sync_every` generations between barriers and the
-    master checks R-hat on every sync block (src/demcz.jl:129-155).  Here every chain is a GPU thread and the barrier is
-    the kernel boundary, so the entry point maps onto the same generation loop with `autostop_every = sync_every`;
-    `workerpool` is accepted and ignored.  Positional defaults follow src/demcz.jl:106 (autostop=:Rhat, Rhat < 1.1).
-    For several GPUs use demc_jl_b200.dist.make_sharded_sampler under torchrun."""
+    In the reference one Distributed.jl worker runs each chain for `sync_every` generations between barriers, all
+    workers append to one shared Z, and the master checks R-hat on every sync block (:129-155).  Here the workers are
+    the GPUs of the box: launched under torchrun (WORLD_SIZE > 1) the call runs the sharded sampler — chains
+    partitioned over the ranks, archive replicated, every rank's appended rows exchanged over NVLink every K
+    generations — and every rank returns the whole (mc, Z) like the reference's master.  `sync_every` is the R-hat
+    check period (autostop_every); rows become visible to the other ranks every K <= sync_every generations, i.e. at
+    least as often as a sync block ends.  `workerpool` is accepted and ignored.  With one process it is the same
+    generation loop on one GPU.  Positional defaults follow src/demcz.jl:106 (autostop=:Rhat, Rhat < 1.1)."""
     if len(args) == 1 and isinstance(args[0], DEMCopt):
         o = args[0]
         kw2 = dict(autostop=o.autostop, autostop_Rhat=o.autostop_Rhat, verbose=o.verbose)
@@ -466,16 +537,19 @@ def demcz_sample_par(logobj, Zmat, *args, sync_every=1000, prevrun=None, workerp
     for name, val in (("autostop", autostop), ("autostop_Rhat", autostop_Rhat), ("verbose", verbose)):
         if val is not None:
             kw2[name] = val
+    kw.setdefault("sharded", True)
     return demcz_sample(logobj, Zmat, *args, prevrun=prevrun, autostop_every=int(sync_every), **kw2, **kw)
 
 
 def demcz_anneal_par(logobj, Zmat, *args, sync_every=1000, prevrun=None, temperaturefun: Callable = tempbaseline, T0=None,
-                     TN=None, adaptγ=None, verbose=None, **kw):
+                     TN=None, adaptγ=None, verbose=None, workerpool=None, **kw):
     """demcz_anneal_par (src/demcz_anneal.jl:82-140): γ is adapted once per sync block there, i.e. adapt_every = sync_every;
-    the positional form defaults to TN = 1e-3 (src/demcz_anneal.jl:86), unlike the serial one."""
+    the positional form defaults to TN = 1e-3 (src/demcz_anneal.jl:86), unlike the serial one.  Under torchrun the
+    chains are sharded over the GPUs like demcz_sample_par (the accept counter of the γ rule is all-reduced)."""
     ad = dict(_ADAPT_DEFAULT) if adaptγ is None else dict(adaptγ)
     ad["adapt_every"] = int(sync_every)
     if not (len(args) == 1 and isinstance(args[0], DEMCopt)) and TN is None:
         TN = 1e-3
+    kw.setdefault("sharded", True)
     return demcz_anneal(logobj, Zmat, *args, prevrun=prevrun, temperaturefun=temperaturefun, T0=T0, TN=TN, adaptγ=ad,
                         verbose=verbose, **kw)

@@ -15,6 +15,7 @@
 // flag word per rank in every peer's allocation publishes the segment.  In overlap mode the push runs on a
 // high-priority side stream under the next K-block's step kernel.
 #include "demcz_internal.h"
+#include "demcz_sync.cuh"
 #include <dlfcn.h>
 #include <unistd.h>
 #include <cstring>
@@ -164,16 +165,9 @@ struct PeerPtrs { float* p[8]; };
 // (16 bytes each) of a slot cross the links.  A small persistent grid (a few CTAs are enough to saturate NVLink
 // with 16-byte stores) so that it shares the SMs with the step kernel it runs under.  When the last CTA is done —
 // all stores fenced at system scope — it publishes the segment: peer r's flag word [my rank] = seq.
-//
-// PACKED (DEMCZ_XCHG_PACKED): the destination is not the slot but `packed_base + 4 t` floats into the peer's
-// allocation — this rank's block of the staging ring, rows back to back.  NVLink moves whole 128-byte lines and a
-// partly written line costs a full one (tools/push_bench.cu: 5.2 G lines/s either way), so 80-byte rows of a
-// 128-byte slot cross the links 1.55x faster packed; the receiver scatters them (unpack_rows_kernel).
-template <bool PACKED>
 __global__ void __launch_bounds__(256)
 push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long long row0, int nrows, int ZS, int C,
-                 unsigned long long packed_base, unsigned long long flag_off_floats, int my_rank, unsigned long long seq,
-                 unsigned int* done_counter)
+                 unsigned long long flag_off_floats, int my_rank, unsigned long long seq, unsigned int* done_counter)
 {
     constexpr int U = 8;                         // independent 16-byte loads in flight per thread
     const long long total = (long long)nrows * C;
@@ -186,9 +180,8 @@ push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long 
             const long long t = t0 + u * stride;
             const long long row = t / C;
             const int piece = (int)(t - row * C);
-            const size_t src = (size_t)(row0 + row) * ZS + piece * 4;
-            off[u] = PACKED ? (size_t)packed_base + (size_t)t * 4 : src;
-            if (t < total) v[u] = __ldcg(reinterpret_cast<const float4*>(Zl + src));
+            off[u] = (size_t)(row0 + row) * ZS + piece * 4;
+            if (t < total) v[u] = __ldcg(reinterpret_cast<const float4*>(Zl + off[u]));
         }
 #pragma unroll
         for (int u = 0; u < U; ++u)
@@ -198,7 +191,10 @@ push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long 
     __threadfence_system();
     __syncthreads();
     __shared__ bool last;
-    if (threadIdx.x == 0) last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+    if (threadIdx.x == 0) {
+        last = (atomicAdd(done_counter, 1u) == gridDim.x - 1);
+        __threadfence();                         // acquire side of the ticket: the other CTAs' (fenced) stores happen-before the flag stores below
+    }
     __syncthreads();
     if (last) {
         if (threadIdx.x == 0) *done_counter = 0u;
@@ -209,48 +205,23 @@ push_rows_kernel(const float* __restrict__ Zl, PeerPtrs peers, int npeers, long 
     }
 }
 
-// Receiver side of the packed exchange: the other ranks' rows of one landed segment, staging ring -> row slots.
-// `stage`: the segment's buffer [N_global][4 C] floats; rows of this rank's own block [own0, own0 + n_own) are already
-// in place (written by the append).  An odd piece count gets its last 32-byte sector completed with slot padding,
-// like the append does (whole sectors need no read-modify-write fill in L2).
-__global__ void __launch_bounds__(256)
-unpack_rows_kernel(const float* __restrict__ stage, float* __restrict__ Zl, long long seg_row0, long long n_rows,
-                   long long own0, long long n_own, int ZS, int C, int CW)
+// Copy-engine transport: the rows went out as one peer copy per rank on the same stream; stream order makes them
+// complete (and visible at the destination) before this kernel starts, which then only publishes the segment.
+__global__ void publish_flags_kernel(PeerPtrs peers, int npeers, unsigned long long flag_off_floats, int my_rank,
+                                     unsigned long long seq)
 {
-    constexpr int U = 4;
-    const long long total = (n_rows - n_own) * CW;
-    const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long t0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; t0 < total; t0 += stride * U) {
-        float4 v[U];
-        size_t dst[U];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const long long t = t0 + u * stride;
-            long long row = t / CW;
-            const int piece = (int)(t - row * CW);
-            if (row >= own0) row += n_own;
-            dst[u] = (size_t)(seg_row0 + row) * ZS + piece * 4;
-            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (t < total && piece < C) v[u] = __ldcg(reinterpret_cast<const float4*>(stage + (size_t)row * (4 * C) + piece * 4));
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u)
-            if (t0 + u * stride < total) *reinterpret_cast<float4*>(Zl + dst[u]) = v[u];
+    if ((int)threadIdx.x < npeers) {
+        __threadfence_system();
+        unsigned long long* f = reinterpret_cast<unsigned long long*>(peers.p[threadIdx.x] + flag_off_floats) + my_rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(seq) : "memory");
     }
 }
 
-// Before a kernel that draws from segment `need - 1`: wait (normally zero spins) until every peer has published it.
+// Stream-ordered wait until every peer has published `need` segments (end of a run; the gathering kernels poll the
+// same words in their own prologue, so no such kernel sits between two K-blocks).
 __global__ void wait_flags_kernel(const unsigned long long* flags, int world, int my_rank, unsigned long long need)
 {
-    const int r = threadIdx.x;
-    if (r >= world || r == my_rank) return;
-    for (unsigned int spin = 0; spin < (1u << 28); ++spin) {
-        unsigned long long v;
-        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
-        if (v >= need) return;
-        __nanosleep(200);
-    }
-    __trap();                                   // a peer never delivered: fail the launch instead of hanging
+    demcz::wait_peer_segments(flags, world, my_rank, need);
 }
 }  // namespace
 
@@ -305,39 +276,20 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
         }
     }
     c->peers_open = true;
-    // every rank takes the same decision (same opts); with dense slots (ZS == LD) the in-place push is already packed
-    const int lay = c->o.exchange_layout;
-    c->xchg_packed = c->ZS != c->LD && lay == DEMCZ_XCHG_PACKED;
-    // overlap mode, rows stored in place: with DEMCZ_FUSED_PUSH=1 the next step-kernel launch carries the push itself
-    // (demcz_step.cuh, PUSH).  Opt-in: measured at parity with the separate kernel on 2 GPUs.
-    const char* env = getenv("DEMCZ_FUSED_PUSH");
-    c->fuse_push = c->o.sync_mode == DEMCZ_SYNC_OVERLAP && !c->xchg_packed && env && atoi(env) == 1;
+    // every rank takes the same decision (same opts).  AUTO: the copy engines when a rank's rows are one contiguous
+    // block of whole lines to every peer... measured choice, see DESIGN.md section 5
+    c->push_engine = c->o.push_engine == DEMCZ_PUSH_COPY_ENGINE ? 1 : 0;
+    if (const char* env = getenv("DEMCZ_PUSH_ENGINE")) c->push_engine = (atoi(env) == DEMCZ_PUSH_COPY_ENGINE) ? 1 : 0;
     return DEMCZ_OK;
 }
 
 // Completes the archive segment starting at physical row `phys_row0` on every rank.  `side`: issue on the side
-// stream with the second communicator (overlap mode), else on the compute stream.
-static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned long long seq);
-
+// stream with the second communicator (overlap mode), else on the compute stream.  The segment's sequence number is
+// appends + 1 (this is segment number `appends`).
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
 {
-    return exchange_seq(c, phys_row0, side, (unsigned long long)c->appends + 1);       // this is segment number `appends`
-}
-
-int demcz_comm_flush_pending_push(demcz_ctx* c)
-{
-    if (!c->push_pending) return DEMCZ_OK;
-    c->push_pending = false;
-    const bool packed = c->xchg_packed;          // (never both; the stand-alone kernel stores in place)
-    c->xchg_packed = false;
-    int rc = exchange_seq(c, c->push_row0, false, c->push_seq);
-    c->xchg_packed = packed;
-    return rc;
-}
-
-static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned long long seq)
-{
     if (c->o.world == 1) return DEMCZ_OK;
+    const unsigned long long seq = (unsigned long long)c->appends + 1;
     if (phys_row0 + c->o.N_global > c->zcap)
         return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "multi-GPU append segment wraps the archive ring; make archive_capacity and M0 multiples of N");
     cudaStream_t st = side ? c->comm_stream : c->stream;
@@ -351,24 +303,26 @@ static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned lon
         PeerPtrs pp;
         int np = 0;
         for (int r = 0; r < c->o.world; ++r) if (r != c->o.rank) pp.p[np++] = c->peerZ[r];
-        const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
-        const long long total = (long long)c->o.N * C;
-        const int grid = (int)std::min<long long>(32, (total + 255) / 256);      // measured: 16..128 CTAs move the same bytes/s (link-bound)
-        unsigned int* done = (unsigned int*)(c->d_barrier + (side ? 1 : 0));
         mark();
-        if (c->xchg_packed) {
-            const int buf = (int)((seq - 1) % kStageDepth);
-            const unsigned long long base = demcz_stage_off_floats(c) + ((size_t)buf * c->o.N_global + c->o.chain_offset) * c->LD;
-            push_rows_kernel<true><<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C, base,
-                                                         demcz_flag_off_floats(c), c->o.rank, seq, done);
+        if (c->push_engine == 1) {
+            // one contiguous copy per peer: this rank's N row slots (with dense slots: payload only)
+            const size_t off = (size_t)(phys_row0 + c->o.chain_offset) * c->ZS;
+            const size_t bytes = (size_t)c->o.N * c->ZS * sizeof(float);
+            for (int r = 0; r < np; ++r)
+                if (cudaMemcpyAsync(pp.p[r] + off, c->dZ + off, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+                    return demcz_fail(c, DEMCZ_ERR_CUDA, "peer copy of the appended rows failed: %s", cudaGetErrorString(cudaGetLastError()));
+            publish_flags_kernel<<<1, 32, 0, st>>>(pp, np, demcz_flag_off_floats(c), c->o.rank, seq);
         } else {
-            push_rows_kernel<false><<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C, 0ull,
-                                                          demcz_flag_off_floats(c), c->o.rank, seq, done);
+            const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
+            const long long total = (long long)c->o.N * C;
+            const int grid = (int)std::min<long long>(32, (total + 255) / 256);      // measured: 16..128 CTAs move the same bytes/s (link-bound)
+            unsigned int* done = (unsigned int*)(c->d_barrier + (side ? 1 : 0));
+            push_rows_kernel<<<grid, 256, 0, st>>>(c->dZ, pp, np, phys_row0 + c->o.chain_offset, c->o.N, c->ZS, C,
+                                                   demcz_flag_off_floats(c), c->o.rank, seq, done);
         }
-        if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "push_rows_kernel launch failed");
+        if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "push launch failed");
         mark();
-        if (!side) return demcz_comm_wait_segment(c, (int64_t)seq);               // strict: publish before the next launch
-        return DEMCZ_OK;
+        return DEMCZ_OK;                   // the next gathering launch polls the flag words itself (demcz_comm_need)
     }
     float* seg = c->dZ + (size_t)phys_row0 * c->ZS;
     const size_t count = (size_t)c->o.N * c->ZS;                 // floats per rank
@@ -377,6 +331,16 @@ static int exchange_seq(demcz_ctx* c, int64_t phys_row0, bool side, unsigned lon
     if (rc != ncclSuccess) return nccl_fail(c, "ncclAllGather", rc);
     mark();
     return DEMCZ_OK;
+}
+
+// Segments that must have landed from every peer before the next launch may gather: every appended segment in strict
+// mode, all but the newest in overlap mode (the newest is still travelling under that launch and is not drawable).
+// Only the peer-push transport uses flag words; the NCCL all-gather is ordered by its stream / events.
+unsigned long long demcz_comm_need(const demcz_ctx* c)
+{
+    if (c->o.world == 1 || !c->peers_open) return 0ull;
+    const int64_t n = c->o.sync_mode == DEMCZ_SYNC_OVERLAP ? c->appends - 1 : c->appends;
+    return n > 0 ? (unsigned long long)n : 0ull;
 }
 
 int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n)
@@ -399,22 +363,7 @@ int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n)
 int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg)
 {
     if (c->o.world == 1 || !c->peers_open || nseg <= 0) return DEMCZ_OK;
-    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(c->dZ + demcz_flag_off_floats(c));
-    wait_flags_kernel<<<1, 32, 0, c->stream>>>(flags, c->o.world, c->o.rank, (unsigned long long)nseg);
+    wait_flags_kernel<<<1, 32, 0, c->stream>>>(demcz_flags(c), c->o.world, c->o.rank, (unsigned long long)nseg);
     if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "wait_flags_kernel launch failed");
-    if (c->xchg_packed) {
-        // segment s was appended at M_base + s N_global; M and appends advance together (demcz_archive_appended)
-        const int64_t M_base = c->M - c->appends * c->o.N_global;
-        const int C = c->LD / 4, CP = c->ZS / 4, CW = C + ((C % 2 == 1 && C < CP) ? 1 : 0);
-        const long long total = (long long)(c->o.N_global - c->o.N) * CW;
-        const int grid = (int)std::min<long long>(148 * 4, (total + 256 * 4 - 1) / (256 * 4));
-        for (; c->unpacked < nseg; ++c->unpacked) {
-            const int64_t s = c->unpacked;
-            const float* stage = c->dZ + demcz_stage_off_floats(c) + (size_t)(s % kStageDepth) * c->o.N_global * c->LD;
-            unpack_rows_kernel<<<grid, 256, 0, c->stream>>>(stage, c->dZ, (M_base + s * c->o.N_global) % c->zcap, c->o.N_global,
-                                                            c->o.chain_offset, c->o.N, c->ZS, C, CW);
-            if (cudaGetLastError() != cudaSuccess) return demcz_fail(c, DEMCZ_ERR_CUDA, "unpack_rows_kernel launch failed");
-        }
-    }
     return DEMCZ_OK;
 }

@@ -10,7 +10,12 @@
 
 enum { DEMCZ_LIK_NONE = -1, DEMCZ_LIK_MVN = 0, DEMCZ_LIK_LINREG = 1 };
 
-struct demcz_linreg_state;   // demcz_linreg.cu
+struct demcz_linreg_state;   // streaming moments (demcz_lib.cu)
+int demcz_moments_begin(demcz_ctx* c);                       // fixes the shift (population mean) at the first generation
+int demcz_moments_add_state(demcz_ctx* c);                   // adds the current SoA state (one generation) — linreg path
+int demcz_moments_get(demcz_ctx* c, double* mean, double* cov, int64_t* n, int32_t reset);
+
+// demcz_linreg.cu
 
 struct demcz_ctx {
     demcz_opts o{};
@@ -21,6 +26,7 @@ struct demcz_ctx {
     int LD = 0;          // archive row stride in floats (d rounded up to 4 -> 16-byte aligned rows)
     int ldx = 0;         // SoA leading dimension (N rounded up to 32)
     int ZS = 0;          // archive row slot in floats (power of two >= LD for the closed-form path)
+    int thin = 1;        // history thinning (opts.thin, at least 1)
     demcz::PhiloxKeys keys{};
     float shift[64] = {0};
 
@@ -86,29 +92,28 @@ struct demcz_ctx {
     bool peers_open = false;
     int64_t appends = 0;                         // archive appends so far (overlap mode: visibility lags by one)
     int64_t vis_waited = 0;
-    bool step_full = false;                      // the closed-form step launches use the single-full-block kernel
-    bool fuse_push = false;                      // overlap + in-place push: issued from inside the next step-kernel launch
-    bool push_pending = false;                   // a segment is appended locally but not pushed yet (fused push)
-    int64_t push_row0 = 0;                       // its physical first row and
-    unsigned long long push_seq = 0;             // the sequence number its flag words will carry
-    bool xchg_packed = false;                    // DEMCZ_XCHG_PACKED in effect: rows travel densely through the staging ring
-    int64_t unpacked = 0;                        // packed exchange: segments 0 .. unpacked-1 have been scattered into the slots
+    int push_engine = 0;                         // 0: our push kernel (SM stores over NVLink), 1: copy engines (one peer copy per rank) + flag kernel
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
+
+    // opts.moments: streaming first / second moments of every generation of every chain (mean_cov_chain of the full
+    // history without the history).  Sums of (x - mom_shift): d_mom = [S1: 64 doubles][S2: 64 x 64 doubles, row-major]
+    double* d_mom = nullptr;
+    float* dmomshift = nullptr;                  // device copy of mom_shift
+    float mom_shift[64] = {0};
+    bool mom_shift_set = false;
+    int64_t mom_gens = 0;                        // generations accumulated (x N_global points each)
 
     std::string err;
     int sticky = 0;
 };
 
 // One device allocation holds the archive and everything the peers write into, so that a single IPC handle maps it:
-//   [zcap row slots][8 x u64 segment flags, 256 B][staging ring: kStageDepth x N_global dense rows of LD floats]   (ring: packed layout)
-// Depth 4: a sender refills buffer s % 4 with segment s + 4 only after its K-block s + 4 started, which needed the
-// receiver's segment s + 2, which the receiver pushes after its K-block s + 2, which started after it unpacked segment s.
-constexpr int kStageDepth = 4;
+//   [zcap row slots][8 x u64 segment flags, 256 B]
 inline size_t demcz_flag_off_floats(const demcz_ctx* c) { return (size_t)c->zcap * c->ZS; }
-inline size_t demcz_stage_off_floats(const demcz_ctx* c) { return (demcz_flag_off_floats(c) + 64 + 31) / 32 * 32; }
-inline size_t demcz_stage_floats(const demcz_ctx* c)     // only the packed layout has a staging ring
+inline size_t demcz_alloc_floats(const demcz_ctx* c) { return (demcz_flag_off_floats(c) + 64 + 31) / 32 * 32; }
+inline const unsigned long long* demcz_flags(const demcz_ctx* c)
 {
-    return (c->o.world > 1 && c->o.exchange_layout == DEMCZ_XCHG_PACKED) ? (size_t)kStageDepth * c->o.N_global * c->LD : 0;
+    return reinterpret_cast<const unsigned long long*>(c->dZ + demcz_flag_off_floats(c));
 }
 
 int demcz_fail(demcz_ctx* c, int code, const char* fmt, ...);
@@ -121,11 +126,17 @@ int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens);
 
 // demcz_comm.cu — no-ops when world == 1
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);
-int demcz_comm_flush_pending_push(demcz_ctx* c);             // fused push: the segment no later launch will carry (end of a run)
-int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);     // + packed exchange: scatters the landed segments into their slots
+int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);     // stream-ordered wait (end of a run; the step kernels poll the flags themselves)
+// how many segments must have landed from every peer before the next gathering launch (0: no wait); see demcz_archive_view
+unsigned long long demcz_comm_need(const demcz_ctx* c);
 int demcz_comm_allreduce_f64(demcz_ctx* c, double* dev, int n);
 int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n);
 void demcz_comm_destroy_internal(demcz_ctx* c);
+
+// streaming moments (demcz_lib.cu)
+int demcz_moments_begin(demcz_ctx* c);                       // fixes the shift (population mean) at the first generation
+int demcz_moments_add_state(demcz_ctx* c);                   // adds the current SoA state (one generation) — linreg path
+int demcz_moments_get(demcz_ctx* c, double* mean, double* cov, int64_t* n, int32_t reset);
 
 // demcz_linreg.cu
 // out_dev == nullptr: evaluate the context's own N chains into its FP64 log-objective array

@@ -165,6 +165,31 @@ __global__ void cov_kernel(const float* __restrict__ X, int n, int ldx, int d, c
     if (threadIdx.x == 0) atomicAdd(&cov[k1 * d + k2], s);
 }
 
+// streaming moments of one generation from the SoA state: S1[k] += sum_i (x_k - s_k), S2[k1][k2] += sum_i (x_k1 - s_k1)(x_k2 - s_k2)
+// grid: (blocks, d * d + d); blockIdx.y < d*d: pair (k1, k2) with k1 <= k2 (others idle), else column sums
+__global__ void state_moments_kernel(const float* __restrict__ X, int n, int ldx, int d, const float* __restrict__ shift,
+                                     double* __restrict__ mom)
+{
+    __shared__ double sm[32];
+    const int y = blockIdx.y;
+    double s = 0.0;
+    if (y < d * d) {
+        const int k1 = y / d, k2 = y % d;
+        if (k1 > k2) return;
+        const float s1 = shift[k1], s2 = shift[k2];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+            s += (double)(X[(size_t)k1 * ldx + i] - s1) * (double)(X[(size_t)k2 * ldx + i] - s2);
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) atomicAdd(&mom[64 + k1 * 64 + k2], s);
+    } else {
+        const int k = y - d * d;
+        const float s1 = shift[k];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (double)(X[(size_t)k * ldx + i] - s1);
+        s = block_sum(s, sm);
+        if (threadIdx.x == 0) atomicAdd(&mom[k], s);
+    }
+}
+
 // archive rows (row-major slots, ring) -> per-column sums / centred cross products, FP64.  grid: (blocks, d) / (blocks, d*d)
 __global__ void rows_colsum_kernel(const float* __restrict__ Z, long long row0, long long n, long long zstart, long long zcap,
                                    int ZS, double* __restrict__ sums)
@@ -195,6 +220,29 @@ __global__ void rows_cov_kernel(const float* __restrict__ Z, long long row0, lon
     }
     s = block_sum(s, sm);
     if (threadIdx.x == 0) atomicAdd(&cov[k1 * d + k2], s);
+}
+
+// 64-bit checksum of archive rows: sum over (logical row i, column k) of mix64(bits(Z[i][k]) ^ (i * 64 + k) * golden).
+// Order-independent (a sum), position-sensitive (the position is mixed in): equal iff the replicas hold the same rows.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+__global__ void rows_checksum_kernel(const float* __restrict__ Z, long long row0, long long n, long long zstart, long long zcap,
+                                     int ZS, int d, unsigned long long* __restrict__ out)
+{
+    unsigned long long h = 0ull;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        long long p = zstart + row0 + i;
+        if (p >= zcap) p -= zcap;
+        for (int k = 0; k < d; ++k)
+            h += mix64((unsigned long long)__float_as_uint(Z[p * ZS + k]) ^ ((unsigned long long)((row0 + i) * 64 + k) * 0x9E3779B97F4A7C15ull));
+    }
+    h = warp_sum(h);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, h);
 }
 
 // Gelman-Rubin partial sums over the local chain-halves (Rhat_gelman, src/utils.jl:2-20):
@@ -285,8 +333,14 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: inconsistent rank/world/N_global/chain_offset");
     if (o->autostop && (o->autostop_every < 4))
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: autostop_every must be >= 4");
-    if (o->exchange_layout < DEMCZ_XCHG_AUTO || o->exchange_layout > DEMCZ_XCHG_DENSE_SLOTS)
-        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: exchange_layout %d", o->exchange_layout);
+    if (o->exchange_layout != DEMCZ_XCHG_AUTO && o->exchange_layout != DEMCZ_XCHG_IN_PLACE && o->exchange_layout != DEMCZ_XCHG_DENSE_SLOTS)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: exchange_layout %d (0 auto, 1 in_place, 3 dense_slots)", o->exchange_layout);
+    if (o->push_engine < DEMCZ_PUSH_AUTO || o->push_engine > DEMCZ_PUSH_COPY_ENGINE)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: push_engine %d", o->push_engine);
+    if (o->thin < 0 || o->moments < 0 || o->moments > 1 || o->persistent < -1 || o->persistent > 1)
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: bad thin/moments/persistent");
+    if (!(o->snooker_prob >= 0.0 && o->snooker_prob <= 1.0) || !(o->snooker_gamma >= 0.0))
+        return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: snooker_prob must be in [0,1], snooker_gamma >= 0");
     if (o->anneal && o->adapt && o->adapt_every < 1)
         return demcz_fail(nullptr, DEMCZ_ERR_INVALID, "demcz_create: adapt_every must be >= 1");
     for (int b = 0; b < o->Nblocks; ++b) {
@@ -343,9 +397,10 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
         alloc((void**)&c->dS2, (size_t)2 * o->d * sizeof(double));
         alloc((void**)&c->dshift, (size_t)o->d * sizeof(float));
     }
-    if (o->store_chain == 1 && o->Ngeneration > 0) {
-        alloc((void**)&c->dhist, (size_t)o->Ngeneration * o->d * o->N * sizeof(float));
-        alloc((void**)&c->dlphist, (size_t)o->Ngeneration * o->N * sizeof(float));
+    c->thin = o->thin > 1 ? o->thin : 1;
+    if (o->store_chain == 1 && o->Ngeneration / c->thin > 0) {
+        alloc((void**)&c->dhist, (size_t)(o->Ngeneration / c->thin) * o->d * o->N * sizeof(float));
+        alloc((void**)&c->dlphist, (size_t)(o->Ngeneration / c->thin) * o->N * sizeof(float));
     }
     if (o->trace && o->Ngeneration > 0) {
         const size_t np = (size_t)o->Ngeneration * o->Nblocks * o->N;
@@ -376,7 +431,7 @@ extern "C" void demcz_destroy(demcz_ctx* c)
     demcz_linreg_free(c);
     void* ptrs[] = {c->dX, c->dlogp, c->dZ, c->dT, c->dhist, c->dlphist, c->tr_r1, c->tr_r2, c->tr_u, c->tr_xprop,
                     c->tr_lpprop, c->tr_acc, c->d_chain_changed, c->d_counters, c->dS1[0], c->dS1[1], c->dS2, c->dshift,
-                    c->d_scratch, c->d_stage};
+                    c->d_scratch, c->d_stage, c->d_mom, c->dmomshift};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t ev : c->ev_pool) cudaEventDestroy(ev);
     for (cudaEvent_t ev : c->ev_xchg) cudaEventDestroy(ev);
@@ -444,17 +499,17 @@ extern "C" int demcz_set_archive(demcz_ctx* c, const double* Z, int64_t M0)
     int64_t cap = o.archive_capacity > 0 ? o.archive_capacity
                                          : M0 + (o.N_global * (int64_t)o.Ngeneration + o.K - 1) / o.K;   // src/demcz.jl:11
     if (cap < M0) cap = M0;
-    if (cap >= (int64_t)1 << 32) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^32 rows", (long long)cap);
+    // 2^31: ring positions are formed as 32-bit sums (logical row + start of the ring) inside the kernels
+    if (cap >= (int64_t)1 << 31) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "set_archive: capacity %lld >= 2^31 rows", (long long)cap);
     if (c->peers_open) return demcz_fail(c, DEMCZ_ERR_INVALID, "set_archive: the peers hold mappings of the current archive; create a new context");
     if (c->dZ) { cudaFree(c->dZ); c->dZ = nullptr; }
     c->zcap = cap;
-    // archive + segment flags written by the peers + staging ring of the packed exchange (demcz_internal.h)
-    CU(c, cudaMalloc((void**)&c->dZ, (demcz_stage_off_floats(c) + demcz_stage_floats(c)) * sizeof(float)));
-    CU(c, cudaMemsetAsync(c->dZ + demcz_flag_off_floats(c), 0, (demcz_stage_off_floats(c) - demcz_flag_off_floats(c)) * sizeof(float), c->stream));
+    // archive + segment flags written by the peers (demcz_internal.h)
+    CU(c, cudaMalloc((void**)&c->dZ, demcz_alloc_floats(c) * sizeof(float)));
+    CU(c, cudaMemsetAsync(c->dZ + demcz_flag_off_floats(c), 0, (demcz_alloc_floats(c) - demcz_flag_off_floats(c)) * sizeof(float), c->stream));
     c->M = M0;
     c->appends = 0;
     c->vis_waited = 0;
-    c->unpacked = 0;
     double* stage = nullptr;
     CU(c, cudaMalloc((void**)&stage, (size_t)M0 * o.d * sizeof(double)));
     cudaError_t e = cudaMemcpyAsync(stage, Z, (size_t)M0 * o.d * sizeof(double), cudaMemcpyHostToDevice, c->stream);
@@ -546,19 +601,26 @@ static int init_state_if_needed(demcz_ctx* c)
 // The rows a proposal may draw from, as (count, physical row of logical row 0).
 //  * overlap sync mode: the newest appended segment is not drawable yet (it is still being exchanged under this
 //    K-block's compute) — on every rank and for every world size, so results do not depend on the sharding;
-//  * ring buffer about to wrap: the N_global oldest rows, which this K-block's own append will overwrite while
-//    other threads may still be gathering, are excluded as well (keeps runs bit-reproducible).
-// Also makes the compute stream wait until the newest drawable segment has landed from every rank.
+//  * ring buffer about to wrap: the oldest rows that can be overwritten while this K-block's threads are still
+//    gathering are excluded: the N_global rows of this K-block's own append and, in overlap mode, N_global more — a
+//    peer may run one K-block ahead and push its NEXT segment into this replica while this rank is still drawing
+//    (it cannot get further: its K-block after that needs the segment this rank appends at the end of this one).
+//    Applied for every world size, so a wrapped run is still independent of the sharding and bit-reproducible.
+// NCCL transport: also makes the compute stream wait (event) until the newest drawable segment has been gathered; the
+// peer-push transport needs no stream operation — the gathering kernels poll the flag words (demcz_comm_need).
 int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart)
 {
     const demcz_opts& o = c->o;
-    const int64_t pend = (o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends > 0) ? o.N_global : 0;
+    const bool overlap = o.sync_mode == DEMCZ_SYNC_OVERLAP;
+    const int64_t pend = (overlap && c->appends > 0) ? o.N_global : 0;
+    const int64_t remaining = (int64_t)o.Ngeneration / o.K - c->appends_run;       // appends this context will still make
+    const int64_t ahead = std::max<int64_t>(0, std::min<int64_t>(overlap ? 2 : 1, remaining));
+    const int64_t T = c->M + ahead * o.N_global;              // rows [M, T) may be written while this K-block draws
     int64_t m, z0;
-    const bool more_appends = c->appends_run < (int64_t)o.Ngeneration / o.K;      // will this context append again?
-    if (more_appends && c->M + o.N_global > c->zcap) {       // the next append overwrites the oldest rows: keep off them
-        z0 = (c->M + o.N_global) % c->zcap;
-        m = c->zcap - o.N_global - pend;
-    } else if (c->M > c->zcap) {                             // wrapped ring, no further append
+    if (T > c->zcap) {                                        // they land on the oldest rows: keep off them
+        z0 = (T - c->zcap) % c->zcap;
+        m = c->zcap - ahead * o.N_global - pend;
+    } else if (c->M > c->zcap) {                              // wrapped ring, no further append
         z0 = c->M % c->zcap;
         m = c->zcap - pend;
     } else {
@@ -568,12 +630,9 @@ int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart)
     if (m < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: fewer than 2 drawable archive rows (M=%lld, capacity=%lld)", (long long)c->M, (long long)c->zcap);
     *Mdraw = (uint32_t)m;
     *zstart = (uint32_t)z0;
-    if (o.world > 1 && o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends >= 2 && c->vis_waited < c->appends - 1) {
-        // segments 0 .. appends-2 become drawable: this rank's own exchange of them must be done (event) and, with the
-        // push transport, every peer's rows must have landed here (flag words)
+    if (o.world > 1 && !c->peers_open && overlap && c->appends >= 2 && c->vis_waited < c->appends - 1) {
+        // segments 0 .. appends-2 become drawable: the side stream's all-gather of them must be done
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 2) & 1], 0));
-        int rc = demcz_comm_wait_segment(c, c->appends - 1);
-        if (rc != DEMCZ_OK) return rc;
         c->vis_waited = c->appends - 1;
     }
     return DEMCZ_OK;
@@ -585,15 +644,7 @@ int demcz_archive_appended(demcz_ctx* c)
     const demcz_opts& o = c->o;
     const int64_t row0 = c->M % c->zcap;
     if (o.world > 1) {
-        if (c->fuse_push && c->lik_kind == DEMCZ_LIK_MVN && c->step_full) {
-            // overlap mode, closed-form path: the next step-kernel launch pushes this segment while it computes
-            // (demcz_run flushes it with the stand-alone kernel if no launch follows)
-            if (row0 + o.N_global > c->zcap)
-                return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "multi-GPU append segment wraps the archive ring; make archive_capacity and M0 multiples of N");
-            c->push_pending = true;
-            c->push_row0 = row0;
-            c->push_seq = (unsigned long long)c->appends + 1;
-        } else if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
+        if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
             const int slot = (int)(c->appends & 1);
             CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
             CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
@@ -611,11 +662,14 @@ int demcz_archive_appended(demcz_ctx* c)
     return DEMCZ_OK;
 }
 
+// History with thinning: generation grel (1-based) is stored iff grel % thin == 0, at index grel / thin - 1.  A launch
+// covering generations (g, g + n_gens] therefore stores indices [g / thin, (g + n_gens) / thin).
 int demcz_hist_begin(demcz_ctx* c, int64_t g, int n_gens, float** hist, void** lphist)
 {
     const demcz_opts& o = c->o;
     *hist = nullptr; *lphist = nullptr;
-    if (!o.store_chain || o.Ngeneration <= 0) return DEMCZ_OK;
+    const int64_t G_st = (int64_t)o.Ngeneration / c->thin;              // stored generations of the whole run
+    if (!o.store_chain || G_st <= 0) return DEMCZ_OK;
     const bool lin = c->lik_kind == DEMCZ_LIK_LINREG;
     if (o.store_chain == 1) {
         *hist = c->dhist;
@@ -633,15 +687,16 @@ int demcz_hist_begin(demcz_ctx* c, int64_t g, int n_gens, float** hist, void** l
             CU(c, cudaEventCreateWithFlags(&c->hs_ev_k[i], cudaEventDisableTiming));
             CU(c, cudaEventCreateWithFlags(&c->hs_ev_c[i], cudaEventDisableTiming));
         }
-        CU(c, cudaHostAlloc((void**)&c->hs_hx, (size_t)o.Ngeneration * dn * sizeof(float), cudaHostAllocDefault));
-        CU(c, cudaHostAlloc(&c->hs_hlp, (size_t)o.Ngeneration * o.N * c->hs_lp_elem, cudaHostAllocDefault));
+        CU(c, cudaHostAlloc((void**)&c->hs_hx, (size_t)G_st * dn * sizeof(float), cudaHostAllocDefault));
+        CU(c, cudaHostAlloc(&c->hs_hlp, (size_t)G_st * o.N * c->hs_lp_elem, cudaHostAllocDefault));
         CU(c, cudaStreamCreateWithFlags(&c->hs_stream, cudaStreamNonBlocking));
     }
     if (n_gens > c->hs_slice_gens) return demcz_fail(c, DEMCZ_ERR_INVALID, "history slice of %d generations > %lld", n_gens, (long long)c->hs_slice_gens);
     const int p = (int)(c->hs_launches & 1);
     if (c->hs_launches >= 2) CU(c, cudaStreamWaitEvent(c->stream, c->hs_ev_c[p], 0));     // the slice's previous content is on the host
-    *hist = c->hs_dx[p] - (size_t)g * dn;                                                 // kernels index with (grel - 1) = g ..
-    *lphist = (char*)c->hs_dlp[p] - (size_t)g * o.N * c->hs_lp_elem;
+    const int64_t h0 = g / c->thin;                                                       // first stored index of this launch
+    *hist = c->hs_dx[p] - (size_t)h0 * dn;                                                // kernels index with the absolute stored index
+    *lphist = (char*)c->hs_dlp[p] - (size_t)h0 * o.N * c->hs_lp_elem;
     return DEMCZ_OK;
 }
 
@@ -651,11 +706,14 @@ int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens)
     if (o.store_chain != 2 || !c->hs_hx) return DEMCZ_OK;
     const size_t dn = (size_t)o.d * o.N;
     const int p = (int)(c->hs_launches & 1);
+    const int64_t h0 = g / c->thin, h1 = (g + n_gens) / c->thin;                          // stored indices [h0, h1)
     CU(c, cudaEventRecord(c->hs_ev_k[p], c->stream));
-    CU(c, cudaStreamWaitEvent(c->hs_stream, c->hs_ev_k[p], 0));
-    CU(c, cudaMemcpyAsync(c->hs_hx + (size_t)g * dn, c->hs_dx[p], (size_t)n_gens * dn * sizeof(float), cudaMemcpyDeviceToHost, c->hs_stream));
-    CU(c, cudaMemcpyAsync((char*)c->hs_hlp + (size_t)g * o.N * c->hs_lp_elem, c->hs_dlp[p], (size_t)n_gens * o.N * c->hs_lp_elem,
-                          cudaMemcpyDeviceToHost, c->hs_stream));
+    if (h1 > h0) {
+        CU(c, cudaStreamWaitEvent(c->hs_stream, c->hs_ev_k[p], 0));
+        CU(c, cudaMemcpyAsync(c->hs_hx + (size_t)h0 * dn, c->hs_dx[p], (size_t)(h1 - h0) * dn * sizeof(float), cudaMemcpyDeviceToHost, c->hs_stream));
+        CU(c, cudaMemcpyAsync((char*)c->hs_hlp + (size_t)h0 * o.N * c->hs_lp_elem, c->hs_dlp[p], (size_t)(h1 - h0) * o.N * c->hs_lp_elem,
+                              cudaMemcpyDeviceToHost, c->hs_stream));
+    }
     CU(c, cudaEventRecord(c->hs_ev_c[p], c->hs_stream));
     c->hs_launches += 1;
     return DEMCZ_OK;
@@ -733,6 +791,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     if (o.world > 1 && !c->comm) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: world=%d but demcz_comm_init was not called", o.world);
     int rc = init_state_if_needed(c);
     if (rc != DEMCZ_OK) return rc;
+    rc = demcz_moments_begin(c);
+    if (rc != DEMCZ_OK) return rc;
 
     if (!c->ev_run[0]) { CU(c, cudaEventCreate(&c->ev_run[0])); CU(c, cudaEventCreate(&c->ev_run[1])); }
     CU(c, cudaEventRecord(c->ev_run[0], c->stream));
@@ -762,6 +822,9 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             else                        { gb = std::min(gb, w0 + every); }
         }
         if (o.anneal && o.adapt) gb = std::min<int64_t>(gb, (g / o.adapt_every + 1) * (int64_t)o.adapt_every);
+        // opts.moments on the closed-form path: one generation per launch, the state is added to the accumulators
+        // after every launch (exact mean_cov_chain of the full history; the linreg path already runs per generation)
+        if (o.moments && c->lik_kind != DEMCZ_LIK_LINREG) gb = g + 1;
         const int n_gens = (int)(gb - g);
         const bool append = (gb % o.K) == 0;
 
@@ -805,22 +868,16 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift2, c->shift, sizeof a.shift2); }
 
             const bool full = o.Nblocks == 1 && a.blocks[0].mask == (o.d == 32 ? 0xFFFFFFFFu : ((1u << o.d) - 1u));
-            c->step_full = full;
-            if (c->push_pending && full) {               // this launch carries the exchange of the last appended segment
-                for (int r = 0; r < o.world; ++r) if (r != o.rank) a.peer[a.npeers++] = c->peerZ[r];
-                a.push_row0 = (uint32_t)c->push_row0;
-                a.flag_off_floats = demcz_flag_off_floats(c);
-                a.my_rank = o.rank;
-                a.push_seq = c->push_seq;
-                a.push_done = (unsigned int*)(c->d_barrier + 1);
-                c->push_pending = false;
-            }
+            a.thin = c->thin;
+            a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank;
+            a.need = demcz_comm_need(c);
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             CU(c, demcz_launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
             rc = demcz_hist_end(c, g, n_gens);
             if (rc != DEMCZ_OK) return rc;
+            if (o.moments) { rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
         }
         c->proposals += (int64_t)n_gens * o.Nblocks * o.N;
 
@@ -851,10 +908,8 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (c->rhat_max < o.autostop_Rhat) stopped = true;
         }
     }
-    if (o.world > 1 && o.sync_mode == DEMCZ_SYNC_OVERLAP) {                  // drain the exchange: the archive is complete when the call returns
-        rc = demcz_comm_flush_pending_push(c);
-        if (rc != DEMCZ_OK) return rc;
-        if (c->appends > 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 1) & 1], 0));
+    if (o.world > 1) {                                                       // drain the exchange: the archive is complete when the call returns
+        if (o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends > 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 1) & 1], 0));
         rc = demcz_comm_wait_segment(c, c->appends);
         if (rc != DEMCZ_OK) return rc;
     }
@@ -928,7 +983,7 @@ static int d2h_as_f64(demcz_ctx* c, const float* src, size_t n, double* dst)
 extern "C" int demcz_get_chain(demcz_ctx* c, double* chain, double* log_obj)
 {
     CHECK_CTX(c);
-    const size_t G = (size_t)c->g_done, N = c->o.N, d = c->o.d;
+    const size_t G = (size_t)(c->g_done / c->thin), N = c->o.N, d = c->o.d;      // stored generations
     if (!c->o.store_chain) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_chain: store_chain was 0");
     if (G == 0) return DEMCZ_OK;
     if (c->o.store_chain == 2) {                        // streamed: FP32 (FP64 log-objective for linreg) pinned host copy -> caller's Float64
@@ -1041,6 +1096,106 @@ extern "C" int demcz_get_archive_moments(demcz_ctx* c, int64_t first_row, int64_
     CU(c, cudaStreamSynchronize(c->stream));
     if (mean) for (int k = 0; k < d; ++k) mean[k] = h[k];
     if (cov) for (int t = 0; t < d * d; ++t) cov[t] = h[d + t] / (double)n_rows;
+    return DEMCZ_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// streaming moments of the full history (opts.moments): flatten_chain + mean_cov_chain (src/utils.jl:22-32, 96-106)
+// ------------------------------------------------------------------------------------------------
+int demcz_moments_begin(demcz_ctx* c)
+{
+    const demcz_opts& o = c->o;
+    if (!o.moments || c->mom_shift_set) return DEMCZ_OK;
+    if (!c->d_mom) {
+        CU(c, cudaMalloc((void**)&c->d_mom, (64 + 64 * 64) * sizeof(double)));
+        CU(c, cudaMemsetAsync(c->d_mom, 0, (64 + 64 * 64) * sizeof(double), c->stream));
+    }
+    // shift = population mean of the state the run starts from (conditioning of the FP32 products only; the same on
+    // every rank: all-reduced), fixed for the life of the accumulators
+    CU(c, cudaMemsetAsync(c->d_scratch, 0, (size_t)o.d * sizeof(double), c->stream));
+    colsum_kernel<<<dim3(std::min(grid1d(o.N), 64), o.d), 256, 0, c->stream>>>(c->dX, o.N, c->ldx, c->d_scratch);
+    CU(c, cudaGetLastError());
+    int rc = demcz_comm_allreduce_f64(c, c->d_scratch, o.d);
+    if (rc != DEMCZ_OK) return rc;
+    double sums[64];
+    CU(c, cudaMemcpyAsync(sums, c->d_scratch, (size_t)o.d * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int k = 0; k < 64; ++k) c->mom_shift[k] = k < o.d ? (float)(sums[k] / (double)o.N_global) : 0.f;
+    if (!c->dmomshift) CU(c, cudaMalloc((void**)&c->dmomshift, 64 * sizeof(float)));
+    CU(c, cudaMemcpyAsync(c->dmomshift, c->mom_shift, 64 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    c->mom_shift_set = true;
+    return DEMCZ_OK;
+}
+
+int demcz_moments_add_state(demcz_ctx* c)
+{
+    const demcz_opts& o = c->o;
+    state_moments_kernel<<<dim3(std::min(grid1d(o.N), 32), o.d * o.d + o.d), 256, 0, c->stream>>>(c->dX, o.N, c->ldx, o.d, c->dmomshift, c->d_mom);
+    CU(c, cudaGetLastError());
+    c->mom_gens += 1;
+    return DEMCZ_OK;
+}
+
+int demcz_moments_get(demcz_ctx* c, double* mean, double* cov, int64_t* n, int32_t reset)
+{
+    const demcz_opts& o = c->o;
+    const int d = o.d;
+    if (n) *n = c->mom_gens * o.N_global;
+    if (!c->d_mom || c->mom_gens == 0) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_history_moments: no generation accumulated yet");
+    double* tmp = nullptr;                                       // all-reduce a copy: the accumulators stay per-rank
+    CU(c, cudaMalloc((void**)&tmp, (64 + 64 * 64) * sizeof(double)));
+    cudaError_t e = cudaMemcpyAsync(tmp, c->d_mom, (64 + 64 * 64) * sizeof(double), cudaMemcpyDeviceToDevice, c->stream);
+    int rc = DEMCZ_OK;
+    if (e == cudaSuccess) rc = demcz_comm_allreduce_f64(c, tmp, 64 + 64 * 64);
+    std::vector<double> h(64 + 64 * 64);
+    if (e == cudaSuccess && rc == DEMCZ_OK) e = cudaMemcpyAsync(h.data(), tmp, h.size() * sizeof(double), cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(tmp);
+    if (rc != DEMCZ_OK) return rc;
+    CU(c, e);
+    const double inv = 1.0 / ((double)c->mom_gens * (double)o.N_global);
+    for (int k = 0; k < d; ++k) if (mean) mean[k] = (double)c->mom_shift[k] + h[k] * inv;
+    if (cov)
+        for (int k1 = 0; k1 < d; ++k1)
+            for (int k2 = 0; k2 < d; ++k2) {
+                const int a = std::min(k1, k2), b = std::max(k1, k2);                 // upper triangle is accumulated
+                cov[k1 + (size_t)d * k2] = h[64 + a * 64 + b] * inv - (h[k1] * inv) * (h[k2] * inv);
+            }
+    if (reset) {
+        CU(c, cudaMemsetAsync(c->d_mom, 0, (64 + 64 * 64) * sizeof(double), c->stream));
+        c->mom_gens = 0;
+    }
+    return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_history_moments(demcz_ctx* c, double* mean, double* cov, int64_t* n, int32_t reset)
+{
+    CHECK_CTX(c);
+    if (!c->o.moments) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_history_moments: opts.moments was 0");
+    return demcz_moments_get(c, mean, cov, n, reset);
+}
+
+extern "C" int demcz_get_archive_checksum(demcz_ctx* c, int64_t first_row, int64_t n_rows, uint64_t* checksum)
+{
+    CHECK_CTX(c);
+    if (!c->archive_set || !checksum) return demcz_fail(c, DEMCZ_ERR_INVALID, "get_archive_checksum: no archive / null output");
+    const int64_t rows = std::min<int64_t>(c->M, c->zcap);
+    if (first_row < 0 || n_rows < 0 || first_row + n_rows > rows)
+        return demcz_fail(c, DEMCZ_ERR_INVALID, "get_archive_checksum: rows [%lld, %lld) outside the %lld valid rows", (long long)first_row,
+                          (long long)(first_row + n_rows), (long long)rows);
+    const int64_t zstart = c->M > c->zcap ? c->M % c->zcap : 0;
+    unsigned long long* acc = reinterpret_cast<unsigned long long*>(c->d_scratch);
+    CU(c, cudaMemsetAsync(acc, 0, sizeof *acc, c->stream));
+    if (n_rows > 0) {
+        const int blocks = (int)std::min<int64_t>((n_rows + 255) / 256, 148 * 8);
+        rows_checksum_kernel<<<blocks, 256, 0, c->stream>>>(c->dZ, first_row, n_rows, zstart, c->zcap, c->ZS, c->o.d, acc);
+        CU(c, cudaGetLastError());
+    }
+    unsigned long long h = 0;
+    CU(c, cudaMemcpyAsync(&h, acc, sizeof h, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    *checksum = h;
     return DEMCZ_OK;
 }
 

@@ -22,6 +22,7 @@
 // same semantics as demcz_step.cuh (reference src/demcz.jl:167-203, 80-93; src/demcz_anneal.jl:142-178).
 #include "demcz_internal.h"
 #include "demcz_step.cuh"
+#include "demcz_sync.cuh"
 #include "demcz_tcgen05.cuh"
 
 #include <cuda.h>
@@ -176,6 +177,8 @@ struct LinArgs {
     const double *b0, *g;
     // trace
     uint32_t *tr_r1, *tr_r2; float *tr_u, *tr_xprop;
+    // multi-GPU: segment flag words to poll before the first gather (demcz_sync.cuh); need = 0: nothing to wait for
+    const unsigned long long* flags; int world, my_rank; unsigned long long need;
 };
 
 // Philox draw, archive gather, x' = x + c (Z[r1]-Z[r2]) + eps .* z on the block (src/demcz.jl:174-188), then the
@@ -184,6 +187,10 @@ struct LinArgs {
 __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
 {
     const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    if (a.need != 0ull) {                              // sharded runs: the newest drawable segment has landed from every peer
+        wait_peer_segments(a.flags, a.world, a.my_rank, a.need);
+        __syncthreads();
+    }
     if (chain >= a.N) return;
     const uint32_t cid = a.chain_offset + (uint32_t)chain;
     const uint32_t g_lo = (uint32_t)a.gen, g_hi = (uint32_t)((unsigned long long)a.gen >> 32);
@@ -269,7 +276,7 @@ struct AccArgs {
     // generation bookkeeping (last block only)
     double* lp_gen0;              // [ldx] log-objective at the start of the generation
     int* chain_changed; unsigned long long *win_changed, *accepted_total; int count_run, count_win;
-    float* hist; double* lphist;
+    float* hist; double* lphist; long long hidx;      // history slot of this generation (thinning), or hist == nullptr
     float* Zw; int ZS; uint32_t append_row0, zcap, chain_offset;
     float* S1; double* S2; const float* shift;
     float* tr_lpprop; uint8_t* tr_acc;
@@ -335,7 +342,7 @@ __global__ void linreg_accept_kernel(const AccArgs a)
                     if (a.hist) {
 #pragma unroll
                         for (int j = 0; j < 8; ++j)
-                            if (k0 + j < a.d) a.hist[((size_t)(a.grel - 1) * a.d + k0 + j) * a.N + chain] = t[j];
+                            if (k0 + j < a.d) a.hist[((size_t)a.hidx * a.d + k0 + j) * a.N + chain] = t[j];
                     }
                     if (a.Zw) {                                // rows are 16-byte aligned; the padding up to 4*ceil(d/4) is written as zeros
                         float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * a.ZS + k0);
@@ -343,7 +350,7 @@ __global__ void linreg_accept_kernel(const AccArgs a)
                         if (k0 + 4 < LD4) dst[1] = make_float4(t[4], t[5], t[6], t[7]);
                     }
                 }
-                if (a.hist) a.lphist[(size_t)(a.grel - 1) * a.N + chain] = lpn;
+                if (a.hist) a.lphist[(size_t)a.hidx * a.N + chain] = lpn;
             }
         }
     }
@@ -687,7 +694,7 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
     CUL(c, cudaMemsetAsync(s->Dlo, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
     CUL(c, cudaMemsetAsync(s->lp64, 0, (size_t)c->ldx * 2 * sizeof(double), c->stream));
-    if (o.store_chain == 1 && o.Ngeneration > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)o.Ngeneration * o.N * sizeof(double)));
+    if (o.store_chain == 1 && o.Ngeneration / c->thin > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)(o.Ngeneration / c->thin) * o.N * sizeof(double)));
 
     // ---- upload (FP64, as the caller holds it), split, OLS reference point -------------------------
     const int P1 = p + 1, npairs = P1 * P1;
@@ -861,6 +868,8 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
             a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
             a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
+            a.flags = demcz_flags(c); a.world = o.world; a.my_rank = o.rank;
+            a.need = (gi == 0 && b == 0) ? demcz_comm_need(c) : 0ull;          // once per archive view
             linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true);
             CUL(c, cudaGetLastError());
 
@@ -884,7 +893,8 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
             q.count_run = (grel != 1) ? 1 : 0;
             q.count_win = (o.anneal && o.adapt && (grel - 1) % o.adapt_every == 0) ? 0 : 1;
-            q.hist = hist; q.lphist = (double*)lphist;
+            const bool keep = hist != nullptr && grel % c->thin == 0;           // history thinning (opts.thin)
+            q.hist = keep ? hist : nullptr; q.lphist = (double*)lphist; q.hidx = grel / c->thin - 1;
             const bool do_append = append && gi == n_gens - 1;
             q.Zw = do_append ? c->dZ : nullptr; q.ZS = c->ZS;
             q.append_row0 = (uint32_t)(c->M % c->zcap); q.zcap = (uint32_t)c->zcap; q.chain_offset = (uint32_t)o.chain_offset;
@@ -893,6 +903,7 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             linreg_accept_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(q);
             CUL(c, cudaGetLastError());
         }
+        if (o.moments) { int rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
     }
     return demcz_hist_end(c, g, n_gens);
 }

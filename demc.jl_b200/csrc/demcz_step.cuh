@@ -27,6 +27,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include "philox.cuh"
+#include "demcz_sync.cuh"
 
 namespace demcz {
 
@@ -59,7 +60,7 @@ struct StepArgs {
     // append (only when the last generation of the launch is a multiple of K)
     float* Zw;                   // archive base for the append, nullptr -> no append
     uint32_t append_row0;        // physical row of global chain 0's new row
-    // history (store_chain): hist[(grel-1)*d + k][chain], lphist[grel-1][chain]
+    // history (store_chain): hist[hidx*d + k][chain], lphist[hidx][chain], hidx = grel/thin - 1
     float* hist;
     float* lphist;
     // trace (tests)
@@ -73,15 +74,13 @@ struct StepArgs {
     float* S1;                   // [d][ldx]  sum_t (x - shift)
     double* S2;                  // [d]       sum_chains sum_t (x - shift)^2
     float2 shift2[16];           // population mean at the start of the window (conditioning only), column pairs
-    // fused archive exchange (PUSH kernels, multi-GPU overlap mode): the rows this rank appended at the end of the
-    // previous launch are stored into the same slots of every peer's archive replica while this launch computes
-    float* peer[7];              // peer archive allocations (peer-mapped), npeers valid
-    int npeers;
-    uint32_t push_row0;          // physical row of GLOBAL chain 0 in the segment being pushed (segments never wrap the ring)
-    unsigned long long flag_off_floats;   // offset of the segment flag words in every allocation
-    int my_rank;
-    unsigned long long push_seq; // value published to peer r's flag word [my_rank] once every row has landed
-    unsigned int* push_done;     // CTA arrival counter (self-resetting)
+    // history thinning: generation grel is stored iff grel % thin == 0, at index grel / thin - 1 (thin >= 1)
+    int thin;
+    // multi-GPU: the segment flag words of THIS rank's archive allocation (written by the peers) and how many
+    // segments must have landed from every peer before this launch may gather (0: nothing to wait for)
+    const unsigned long long* flags;
+    int world, my_rank;
+    unsigned long long need;
 };
 
 // Packed-FP32 (f32x2) arithmetic: one issue slot per two FMAs (SASS FFMA2 / FADD2 / FMUL2 on sm_100a).
@@ -229,13 +228,7 @@ __device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ Wc, c
 // rows that straddle a 128-byte line (measured 1.39x the DRAM bytes per row for d = 20), but a rank's appended rows
 // are contiguous, so they cross NVLink as whole lines — the layout of choice when the exchange, not the gather,
 // bounds the K-block (8 GPUs).
-// PUSH: compute fused with the exchange.  Each warp re-reads its own 32 rows of the segment appended by the previous
-// launch (L2-resident: they were the last thing written) with consecutive lanes on consecutive 16-byte pieces, and
-// stores them to the peers' replicas over NVLink, a few instructions after every proposal so that the transfer is
-// spread over the whole launch; the last CTA to finish publishes the segment in every peer's flag words.  No second
-// kernel competing for SM slots, no stream hand-offs (the separate push_rows_kernel remains for strict mode, block
-// updates and the last segment of a run).
-template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false, bool PUSH = false>
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
@@ -251,7 +244,6 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     __shared__ float red_s2[ACC ? LD : 1];
     __shared__ __align__(16) float2 scW[W_SMEM ? NWC + H : 1];
     __shared__ float2 s2s[S2_SMEM ? H * WARPS * 32 : 1];
-    __shared__ float* s_peer[PUSH ? 8 : 1];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* wbase = smem + warp * (STAGES * SL::FLOATS);
@@ -265,7 +257,8 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     // rows, counters) — nothing written by a kernel is read or overwritten above this line
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     asm volatile("griddepcontrol.wait;" ::: "memory");
-    if (PUSH && threadIdx.x < 7) s_peer[threadIdx.x] = a.peer[threadIdx.x];
+    // sharded runs: the newest drawable segment must have landed from every peer (normally it has: zero spins)
+    wait_peer_segments(a.flags, a.world, a.my_rank, a.need);
     if (threadIdx.x < 2) red_cnt[threadIdx.x] = 0u;
     if (ACC && threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
     if (W_SMEM)
@@ -343,37 +336,6 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
 
     if (0 < Q) prefetch(0);
     cp_async_commit();
-
-    // ---- fused push: the warp's 32 rows (= the state this launch starts from) are stashed in shared memory; unit j =
-    // (peer j / C, pieces (j % C) * 32 .. + 31 of the stash), consecutive lanes on consecutive 16-byte pieces of a row.
-    // The units are spread over the proposals (not the last one when there are several: the stores are acknowledged
-    // by the time the launch ends).
-    const int push_units = PUSH ? a.npeers * C : 0;
-    const int push_Q = Q > 1 ? Q - 1 : 1;
-    float* stash = smem + WARPS * (STAGES * SL::FLOATS) + warp * (32 * LDS);
-    const size_t push_dst = PUSH ? ((size_t)a.push_row0 + a.chain_offset + (size_t)(blockIdx.x * (WARPS * 32) + warp * 32)) * ZS : 0;
-    const int warp_rows = PUSH ? min(32, a.N - (int)(blockIdx.x * (WARPS * 32) + warp * 32)) : 0;   // ragged last warp (may be <= 0)
-    if (PUSH) {
-        float4* sp = reinterpret_cast<float4*>(stash + lane * LDS);
-#pragma unroll
-        for (int c = 0; c < C; ++c) sp[c] = make_float4(x2[2 * c].x, x2[2 * c].y, x2[2 * c + 1].x, x2[2 * c + 1].y);
-        __syncwarp();
-    }
-    int push_j = 0, push_acc = 0;                             // Bresenham: push_units units over push_Q proposals, no division
-    auto push_some = [&]() {
-        push_acc += push_units;
-        while (push_acc >= push_Q && push_j < push_units) {
-            push_acc -= push_Q;
-            const int r = push_j / C;
-            const int pc = (push_j - r * C) * 32 + lane;      // piece number inside the warp's rows
-            const int row = pc / C;
-            const int off = (pc - row * C) * 4;
-            if (row < warp_rows)
-                *reinterpret_cast<float4*>(s_peer[r] + push_dst + (size_t)row * ZS + off) =
-                    *reinterpret_cast<const float4*>(stash + row * LDS + off);
-            ++push_j;
-        }
-    };
 
     // ---- consumer ---------------------------------------------------------------------------
     int cg = 0, cb = 0;
@@ -453,18 +415,18 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         lp = acc ? lpp : lp;
         cnt_acc += (acc && active) ? 1 : 0;
         __syncwarp();                            // stage q&1 is free for the next prefetch
-        if (PUSH) push_some();
 
         if (FULL || ++cb == nb) {                // end of generation: runchain! bookkeeping (src/demcz.jl:84-87)
             cb = 0;
             const bool changed = active && (lp != lp_gen0);
             cnt_run += (changed && cg != a.run_skip_gi) ? 1 : 0;
             cnt_win += (changed && cg != a.win_skip_gi) ? 1 : 0;
-            if (a.hist && active) {
+            if (a.hist && active && (a.thin <= 1 || grel % a.thin == 0)) {
+                const size_t hi = (size_t)(a.thin <= 1 ? grel : grel / a.thin) - 1;      // thinned history index
 #pragma unroll
                 for (int k = 0; k < LD; ++k)
-                    if (k < a.d) a.hist[((size_t)(grel - 1) * a.d + k) * a.N + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
-                a.lphist[(size_t)(grel - 1) * a.N + chain] = lp;
+                    if (k < a.d) a.hist[(hi * a.d + k) * a.N + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
+                a.lphist[hi * a.N + chain] = lp;
             }
             if (ACC) {
 #pragma unroll
@@ -522,23 +484,6 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     }
     if (ACC && threadIdx.x < a.d) atomicAdd(&a.S2[threadIdx.x], (double)red_s2[threadIdx.x]);
 
-    if (PUSH) {                                  // publish: every store of every CTA fenced at system scope, then the flag words
-        while (push_j < push_units) push_some();               // (only if the launch had fewer proposals than planned for)
-        __syncthreads();                                        // the CTA's stores happen-before thread 0's fence (cumulative release)
-        __shared__ bool last;
-        if (threadIdx.x == 0) {
-            __threadfence_system();
-            last = (atomicAdd(a.push_done, 1u) == gridDim.x - 1);
-        }
-        __syncthreads();
-        if (last) {
-            if (threadIdx.x == 0) *a.push_done = 0u;
-            if ((int)threadIdx.x < a.npeers) {
-                unsigned long long* f = reinterpret_cast<unsigned long long*>(s_peer[threadIdx.x] + a.flag_off_floats) + a.my_rank;
-                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(a.push_seq) : "memory");
-            }
-        }
-    }
 }
 
 // Batched log-density: map(logobj, rows) (src/demcz.jl:17).  X SoA [k][ldx].

@@ -1,5 +1,5 @@
 // demcz_step_launch.cu — instantiations and launch of the fused step kernel (demcz_step.cuh).  Compiled once per
-// register-width group (-DDEMCZ_LD_GROUP=0..3) so that the build parallelises: every (LD, ACC, FULL, DENSE, PUSH)
+// register-width group (-DDEMCZ_LD_GROUP=0..3) so that the build parallelises: every (LD, ACC, FULL, DENSE)
 // combination is its own kernel.
 #include "demcz_step_host.h"
 #include <cstdlib>
@@ -16,12 +16,12 @@ constexpr int kStepOpt = DEMCZ_STEP_OPT;
 // resident blocks per SM the register allocation is held to (4 warps per block)
 template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
 
-template <int LD, bool ACC, bool FULL, bool DENSE, bool PUSH = false>
+template <int LD, bool ACC, bool FULL, bool DENSE>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE, PUSH>;
-    const size_t smem = (size_t)kWarps * (2 * SL::FLOATS + (PUSH ? 32 * SL::LDS : 0)) * sizeof(float);   // + the fused push's row stash
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE>;
+    const size_t smem = (size_t)kWarps * (2 * SL::FLOATS) * sizeof(float);
     static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
     const int dev = c->device & 63;
     if (!configured[dev]) {
@@ -49,8 +49,6 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 template <int LD, bool DENSE>
 cudaError_t launch_step_lay(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
-    if (full && a.npeers > 0)                   // fused push (full-block launches only; demcz_archive_appended arranges that)
-        return acc ? launch_step_t<LD, true, true, DENSE, true>(c, a) : launch_step_t<LD, false, true, DENSE, true>(c, a);
     if (full) return acc ? launch_step_t<LD, true, true, DENSE>(c, a) : launch_step_t<LD, false, true, DENSE>(c, a);
     return acc ? launch_step_t<LD, true, false, DENSE>(c, a) : launch_step_t<LD, false, false, DENSE>(c, a);
 }

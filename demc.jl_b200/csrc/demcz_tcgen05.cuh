@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include "demcz_sync.cuh"
 
 namespace demcz { namespace tc {
 
@@ -31,17 +32,24 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// Bounded wait: a protocol bug must end as a launch failure, never as a hung GPU.
+// Bounded wait: a protocol bug must end as a launch failure, never as a hung GPU.  The bound is WALL time (20 s on
+// %globaltimer, sampled every 4096 polls), not a poll count: a healthy launch that is time-sliced, preempted or run
+// under a debugger must not trap.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
 {
     const uint32_t a = smem_u32(bar);
     uint32_t done = 0;
-    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+    unsigned long long t0 = 0;
+    for (uint32_t spin = 0;; ++spin) {
         asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
                      : "=r"(done) : "r"(a), "r"(parity) : "memory");
         if (done) return;
+        if ((spin & 4095u) == 4095u) {
+            const unsigned long long t = global_timer_ns();
+            if (t0 == 0) t0 = t;
+            else if (t - t0 > kSpinTimeoutNs) __trap();
+        }
     }
-    __trap();
 }
 
 // ---- TMA: 2-D tiled load global -> shared, completion on an mbarrier ------------------------------

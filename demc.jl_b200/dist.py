@@ -14,7 +14,8 @@ from typing import Optional, Tuple
 
 import numpy as np
 
-__all__ = ["shard", "env_rank_world", "broadcast_unique_id", "make_sharded_sampler", "open_peer_archives"]
+__all__ = ["shard", "env_rank_world", "broadcast_unique_id", "make_sharded_sampler", "open_peer_archives",
+           "ensure_process_group", "pad_archive_for_sharding", "allgather_rows", "allreduce_sum"]
 
 
 def shard(N_global: int, rank: int, world: int) -> Tuple[int, int]:
@@ -90,3 +91,53 @@ def open_peer_archives(s, rank=None, world=None, device=None, group=None):
     allinfo = [torch.zeros(128, dtype=torch.uint8, device=dev) for _ in range(world)]
     dist.all_gather(allinfo, mine, group=group)
     s.open_peers(b"".join(bytes(t.cpu().numpy().tobytes()) for t in allinfo))
+
+
+def ensure_process_group(local_rank=0):
+    """Initialise torch.distributed from the torchrun environment if the caller has not (NCCL when CUDA is there)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_initialized():
+        return
+    if torch.cuda.is_available():
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    else:
+        dist.init_process_group("gloo")
+
+
+def pad_archive_for_sharding(Zmat, N_global, Ngeneration, K):
+    """A rank's appended segment must not straddle the end of the archive ring (demcz_comm.cu): make M0 and the capacity
+    multiples of N by repeating the oldest rows in front (they stay ordinary archive members, drawn like any other row).
+    Returns (Zmat_padded, capacity)."""
+    M0 = Zmat.shape[0]
+    pad = (-M0) % N_global
+    if pad:
+        Zmat = np.asfortranarray(np.concatenate([Zmat[:pad], Zmat], axis=0))
+    cap = Zmat.shape[0] + N_global * (-(-Ngeneration // K))
+    return Zmat, cap
+
+
+def _dev(local_rank):
+    import torch
+    import torch.distributed as dist
+    return torch.device("cuda", local_rank) if dist.get_backend() == "nccl" else torch.device("cpu")
+
+
+def allgather_rows(a, local_rank=0):
+    """Concatenate every rank's array along axis 0 (rank order = global chain order); equal shapes on all ranks."""
+    import torch
+    import torch.distributed as dist
+    a = np.ascontiguousarray(a)
+    t = torch.from_numpy(a).to(_dev(local_rank))
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return np.concatenate([o.cpu().numpy() for o in out], axis=0)
+
+
+def allreduce_sum(x, local_rank=0):
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(x)], dtype=torch.float64, device=_dev(local_rank))
+    dist.all_reduce(t)
+    return float(t.item())

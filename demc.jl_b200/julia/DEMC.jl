@@ -69,6 +69,8 @@ struct COpts
     trace::Int32; profile::Int32
     rank::Int32; world::Int32; N_global::Int64; chain_offset::Int64
     sync_mode::Int32; exchange_layout::Int32
+    push_engine::Int32; thin::Int32; moments::Int32; persistent::Int32
+    snooker_prob::Float64; snooker_gamma::Float64
 end
 
 struct CRunInfo
@@ -92,7 +94,8 @@ register(ctx, f) = throw(ArgumentError("logobj must be a registered GPU likeliho
 tempbaseline(ig, Ng, T0, TN) = T0 * (TN / T0)^(ig / Ng)          # src/demcz_anneal.jl:1-3
 
 function run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale, γ; anneal, prevrun, autostop, autostop_Rhat,
-                 autostop_every, T0, TN, temperaturefun, adaptγ, seed=UInt64(31953150), device=0, store_chain=true)
+                 autostop_every, T0, TN, temperaturefun, adaptγ, seed=UInt64(31953150), device=0, store_chain=true,
+                 thin=1, moments=false, snooker_prob=0.0, snooker_gamma=0.0)
     d = size(Zmat, 2)
     bp = Int32[0; cumsum(Int32[length(b) for b in blockindex])]
     bi = Int32[k - 1 for b in blockindex for k in b]                 # 1-based Julia -> 0-based ABI
@@ -102,7 +105,8 @@ function run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale
         o = COpts(sizeof(COpts), N, K, Ngeneration, Nblocks, d, pointer(bp), pointer(bi), pointer(eps), γ, T0, TN,
                   anneal, (autostop == :Rhat && !anneal), autostop_every, autostop_Rhat,
                   (anneal && get(adaptγ, "adapt", false)), get(adaptγ, "minγ", 0.1), get(adaptγ, "maxγ", 4.0), get(adaptγ, "adapt_every", 500),
-                  seed, gen_offset, store_chain, 0, 0, 0, 0, 0, 1, N, 0, 0, 0)
+                  seed, gen_offset, store_chain, 0, 0, 0, 0, 0, 1, N, 0, 0, 0,
+                  0, thin, moments, -1, snooker_prob, snooker_gamma)
         ctxref = Ref{Ptr{Cvoid}}(C_NULL)
         rc = ccall((:demcz_create, libdemcz), Cint, (Ref{Ptr{Cvoid}}, Ref{COpts}, Cint), ctxref, Ref(o), device)
         rc == 0 || error("demcz_create: " * unsafe_string(ccall((:demcz_last_error, libdemcz), Cstring, (Ptr{Cvoid},), C_NULL)))
@@ -122,7 +126,7 @@ function run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale
         end
         info = Ref(CRunInfo(0, 0, 0, 0, 0.0, 0.0, 0, 0, 0, 0, 0.0, 0.0, 0.0, 0))
         check(ctx, ccall((:demcz_run, libdemcz), Cint, (Ptr{Cvoid}, Int64, Ref{CRunInfo}), ctx, 0, info))
-        G = Int(info[].generations_total)
+        G = Int(info[].generations_total) ÷ thin                         # stored generations (opts.thin)
         chain = zeros(N, d, store_chain ? G : 0); log_obj = zeros(N, store_chain ? G : 0)
         store_chain && G > 0 && check(ctx, ccall((:demcz_get_chain, libdemcz), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), ctx, chain, log_obj))
         X = zeros(N, d); lp = zeros(N)

@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define DEMCZ_VERSION 100   /* 0.1.0 */
+#define DEMCZ_VERSION 200   /* 0.2.0 */
 #define DEMCZ_MAX_DIM 32    /* register-resident closed-form likelihood path */
 #define DEMCZ_MAX_DIM_LINREG 64
 
@@ -46,17 +46,20 @@ enum { DEMCZ_INIT_LAST_N_OF_Z = 0, DEMCZ_INIT_REF_SERIAL_ZEROS = 1 };   /* SURVE
  * OVERLAP: they become drawable one K-block later, on every rank and for every world size (also 1), so that the
  * exchange of a segment runs under the next K-block's compute; results are still independent of the sharding. */
 enum { DEMCZ_SYNC_STRICT = 0, DEMCZ_SYNC_OVERLAP = 1 };
-/* How a rank's appended rows travel to the peers' archive replicas once demcz_comm_open_peers was called.  A row of
- * d <= 32 floats sits in a power-of-two slot (32/64/128 bytes) and NVLink moves whole 128-byte lines (a partial
- * line costs a full one: 5.2 G lines/s measured), so
- *   IN_PLACE: stored straight into the peers' slots (no second pass; best while the push hides under compute),
- *   PACKED  : stored densely into a staging ring next to each peer's archive (up to 1.6x fewer lines on the links)
- *             and scattered into the slots by the receiver before the segment becomes drawable,
- *   DENSE_SLOTS: no padding at all — the archive keeps rows back to back (slot = 4*ceil(d/4) floats), so the in-place
- *             push is already dense and nothing is scattered; the gather pays for rows that straddle a line instead
- *             (1.39x the DRAM bytes per row at d = 20).  Fixed at demcz_create (it is the archive layout),
- *   AUTO    : DENSE_SLOTS when world > 4, else IN_PLACE.  Results are identical in every layout. */
-enum { DEMCZ_XCHG_AUTO = 0, DEMCZ_XCHG_IN_PLACE = 1, DEMCZ_XCHG_PACKED = 2, DEMCZ_XCHG_DENSE_SLOTS = 3 };
+/* How a rank's appended rows are laid out in the (replicated) archive and therefore how they cross NVLink once
+ * demcz_comm_open_peers was called.  A row of d <= 32 floats normally sits in a power-of-two slot (32/64/128 bytes) so
+ * that a gather never straddles a 128-byte line; NVLink also moves whole 128-byte lines (a partial line costs a full
+ * one: 5.2 G lines/s measured), so
+ *   IN_PLACE   : rows stored straight into the peers' padded slots (best while the push hides under compute),
+ *   DENSE_SLOTS: no padding — the archive keeps rows back to back (slot = 4*ceil(d/4) floats), a rank's appended rows
+ *                are one contiguous block and cross the links as whole lines; the gather pays for rows that straddle
+ *                a line instead (1.39x the DRAM bytes per row at d = 20).  Fixed at demcz_create (it is the layout),
+ *   AUTO       : DENSE_SLOTS when world > 4, else IN_PLACE.  Results are identical in every layout.
+ * (Value 2 was the `packed` staging-ring exchange of version 100; removed: never better than DENSE_SLOTS.) */
+enum { DEMCZ_XCHG_AUTO = 0, DEMCZ_XCHG_IN_PLACE = 1, DEMCZ_XCHG_DENSE_SLOTS = 3 };
+/* Who moves the rows: our push kernel (SM-issued 16-byte stores into every peer replica) or the copy engines (one
+ * contiguous peer copy per rank and segment, no SM time; flags published by a one-warp kernel behind the copies). */
+enum { DEMCZ_PUSH_AUTO = 0, DEMCZ_PUSH_KERNEL = 1, DEMCZ_PUSH_COPY_ENGINE = 2 };
 
 /* Mirror of DEMCopt (src/DEMC.jl:24-39) + the keyword arguments of demcz_sample (src/demcz.jl:9)
  * and demcz_anneal (src/demcz_anneal.jl:18), as a POD.  Field meaning == reference option of the
@@ -94,7 +97,18 @@ typedef struct {
     int64_t N_global;
     int64_t chain_offset;       /* global id of local chain 0 (Philox counter, archive row order) */
     int32_t sync_mode;          /* DEMCZ_SYNC_* */
-    int32_t exchange_layout;    /* DEMCZ_XCHG_* (was reserved = 0 -> AUTO) */
+    int32_t exchange_layout;    /* DEMCZ_XCHG_* (0 -> AUTO) */
+    /* ---- version 200 ---- */
+    int32_t push_engine;        /* DEMCZ_PUSH_* (0 -> AUTO) */
+    int32_t thin;               /* history thinning (store_chain != 0): generation g is kept iff g % thin == 0, so MC.chain is
+                                   N x d x floor(G/thin); 0 or 1 = every generation (the reference's behaviour) */
+    int32_t moments;            /* 1: accumulate the first and second moments of EVERY generation of every chain on the device
+                                   (demcz_get_history_moments = mean_cov_chain of the full history without keeping it) */
+    int32_t persistent;         /* small N (one CTA): 1 = run all K-blocks between two host decisions in ONE launch, appends made
+                                   visible by a CTA barrier; 0 = one launch per K-block; -1 = auto (on when it applies) */
+    double snooker_prob;        /* probability that a generation uses the snooker update of ter Braak & Vrugt (2008), chosen per
+                                   generation from the Philox stream; 0 = never (the reference implements the parallel update only) */
+    double snooker_gamma;       /* snooker jump size; 0 -> 1.7 */
 } demcz_opts;
 
 typedef struct {
@@ -159,6 +173,14 @@ int demcz_get_moments(demcz_ctx* ctx, double* mean, double* cov);
  * appended during a run are the population every K-th generation, so this is mean_cov_chain (src/utils.jl:96-106) of
  * the K-thinned history without keeping MC.chain: the posterior summary for runs with store_chain = 0. */
 int demcz_get_archive_moments(demcz_ctx* ctx, int64_t first_row, int64_t n_rows, double* mean, double* cov);
+/* mean / covariance (1/n normalisation) over every generation of every chain since create (or since the last call
+ * with reset != 0): flatten_chain + mean_cov_chain (src/utils.jl:22-32, 96-106) of the FULL history from streaming
+ * device accumulators — no MC.chain needed.  Needs opts.moments = 1.  *n = points accumulated (N_global * generations). */
+int demcz_get_history_moments(demcz_ctx* ctx, double* mean, double* cov, int64_t* n, int32_t reset);
+/* 64-bit order-independent checksum of archive rows [first_row, first_row + n_rows) in logical order (bit patterns of
+ * the FP32 rows mixed with their logical position): equal on every rank of a sharded run iff the replicas are identical.
+ * No reference counterpart (the reference shares one Z through a SharedArray, src/demcz.jl:109). */
+int demcz_get_archive_checksum(demcz_ctx* ctx, int64_t first_row, int64_t n_rows, uint64_t* checksum);
 /* last split-Rhat vector (Rhat_gelman, src/utils.jl:2-20), d values */
 int demcz_get_rhat(demcz_ctx* ctx, double* rhat);
 /* per-chain count of generations (2..G of this context) whose log-objective changed:

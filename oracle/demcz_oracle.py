@@ -129,19 +129,23 @@ class LinRegLik:
 # One generation, all chains, generation-synchronous archive (update_blocks ->
 # update_demcz_chain_block -> accept: src/demcz.jl:167-203; tempered: src/demcz_anneal.jl:142-178)
 # ------------------------------------------------------------------------------------------------
-def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0):
+def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0, chain_ids=None,
+                 zstart=0, zcap=None):
     """update_demcz_chain_block for every chain (src/demcz.jl:174-195; tempered src/demcz_anneal.jl:149-170).
 
     X (N,d), lp (N,) are the states ENTERING block ib; returns a dict with r1, r2, u, xprop, lp_prop,
-    accepted and margin = (lp_prop - lp) - T*log(u)  (accept <=> margin > 0; T=1 when T is None)."""
+    accepted and margin = (lp_prop - lp) - T*log(u)  (accept <=> margin > 0; T=1 when T is None).
+    chain_ids: the global chain id of every row of X (default chain_offset + 0..N-1) — lets a checker replay a sample
+    of a large population.  zstart/zcap: logical row r of the drawable view lives at Z[(zstart + r) % zcap] (ring)."""
     X = np.asarray(X, dtype=np.float64)
     lp = np.asarray(lp, dtype=np.float64)
     N, d = X.shape
     key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
-    cid = np.arange(N, dtype=np.uint64) + np.uint64(chain_offset)
+    cid = (np.arange(N, dtype=np.uint64) if chain_ids is None else np.asarray(chain_ids, dtype=np.uint64)) + np.uint64(chain_offset)
     block = np.asarray(block, dtype=np.int64)
     w = philox4x32_10(counters(cid, gen_abs, ib, 0), key)
     r1, r2 = draw_pair(w[:, 0], w[:, 1], M)                                # :176-179
+    p1, p2 = (r1, r2) if zcap is None else ((r1 + zstart) % zcap, (r2 + zstart) % zcap)
     blocklen = block.size
     c = gamma if blocklen == 1 else gamma / math.sqrt(2.0 * blocklen)      # :183-187
     zn = {}
@@ -151,7 +155,7 @@ def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T
         if q not in zn:                                                    # randn(blocklen) :186
             wn = philox4x32_10(counters(cid, gen_abs, ib, 1 + q), key)
             zn[q] = [z for j in range(4) for z in box_muller16(wn[:, j])]   # columns 8q .. 8q+7
-        diff = c * (Z[r1, k] - Z[r2, k]) + eps_scale[k] * zn[q][int(k) & 7]
+        diff = c * (Z[p1, k] - Z[p2, k]) + eps_scale[k] * zn[q][int(k) & 7]
         Xp[:, k] = X[:, k] + diff                                          # :188
     lpp = lik.logdensity(Xp)                                               # :189
     u = uniform(w[:, 2])

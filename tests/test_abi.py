@@ -33,7 +33,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_version_and_struct_sizes():
     lib = _lib.load()
-    assert lib.demcz_version() == 100
+    assert lib.demcz_version() == 200
     # the library rejects a mismatching struct_size: proves both sides agree on sizeof(demcz_opts)
     o = _lib.Opts()
     o.struct_size = C.sizeof(_lib.Opts) - 4
@@ -143,9 +143,13 @@ def test_create_rejects_unknown_exchange_layout():
     ctx = C.c_void_p()
     assert lib.demcz_create(C.byref(ctx), C.byref(o), 0) == -1
     assert b"exchange_layout" in lib.demcz_last_error(None)
-    with pytest.raises(KeyError):
-        DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(2), np.eye(2)), 2, N=4, K=10, Ngeneration=10, blockindex=[[0, 1]],
-                     eps_scale=np.ones(2), γ=2.38, exchange_layout="bogus")
+    o.exchange_layout = 2                            # the removed `packed` staging-ring exchange
+    assert lib.demcz_create(C.byref(ctx), C.byref(o), 0) == -1
+    assert b"exchange_layout" in lib.demcz_last_error(None)
+    for bad in ("bogus", "packed"):
+        with pytest.raises(ValueError):
+            DEMC.Sampler(DEMC.MvNormalLogpdf(np.zeros(2), np.eye(2)), 2, N=4, K=10, Ngeneration=10, blockindex=[[0, 1]],
+                         eps_scale=np.ones(2), γ=2.38, exchange_layout=bad)
 
 
 def test_extract_best_returns_first_maximum_of_the_history():

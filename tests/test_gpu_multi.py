@@ -82,32 +82,8 @@ def test_two_gpus_reproduce_one_gpu_bitwise(sync_mode, p2p):
 _one_gpu_cache = {}
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("d,sync_mode,layout,fused", [
-    (10, "strict", "packed", 0), (10, "overlap", "packed", 0), (13, "overlap", "packed", 0),
-    (20, "strict", "dense_slots", 0), (20, "overlap", "packed", 0), (20, "overlap", "dense_slots", 0),
-    (20, "overlap", "dense_slots", 1), (20, "overlap", "in_place", 1), (10, "overlap", "in_place", 1)])
-def test_two_gpus_exchange_layouts_bitwise(d, sync_mode, layout, fused, monkeypatch):
-    """The ways a rank's appended rows reach the peers' replicas — packed through the staging ring and scattered by
-    the receiver (d = 10: 3 pieces in a 4-piece slot, d = 20: 5 in 8, d = 13: 4 in 4 -> stays in place), an archive
-    without slot padding (dense_slots), and the push fused into the step kernel (DEMCZ_FUSED_PUSH=1) — all give the
-    state / archive / accept counts of one GPU bit for bit.  More K-blocks than the staging ring is deep; two run
-    calls, so that the drain between them (and the stand-alone push of the last segment) is exercised."""
-    monkeypatch.setenv("DEMCZ_FUSED_PUSH", str(fused))
-    N, K, G = 512, 3, 36
-    S = 0.3 * np.ones((d, d)) + 0.7 * np.eye(d)
-    mu = np.linspace(-1, 1, d)
-    Z0 = np.random.default_rng(d).normal(size=(2 * N, d))
-    kw = dict(K=K, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.38, seed=11,
-              store_chain=False, sync_mode=sync_mode)
-    if (d, sync_mode) not in _one_gpu_cache:
-        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, device=0, **kw) as s:
-            s.set_archive(Z0)
-            s.run(G // 2)
-            info1 = s.run()
-            _one_gpu_cache[(d, sync_mode)] = (s.get_state(), s.get_archive(), info1["accepted"])
-    (X1, lp1), Z1, acc1 = _one_gpu_cache[(d, sync_mode)]
-
+def _two_rank_run(make_logobj, d, Z0, N, kw, chunks, **rank_kw):
+    """Two contexts on two GPUs (threads), peer-push transport; returns [(X, lp, Z, info)] per rank."""
     lib = _lib.load()
     buf = (C.c_uint8 * 128)()
     assert lib.demcz_comm_unique_id(buf) == 0
@@ -118,18 +94,18 @@ def test_two_gpus_exchange_layouts_bitwise(d, sync_mode, layout, fused, monkeypa
     def work(r):
         try:
             n_loc, off = ddist.shard(N, r, world)
-            s = DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=n_loc, rank=r, world=world, N_global=N, chain_offset=off,
-                             device=r, exchange_layout=layout, **kw)
+            s = DEMC.Sampler(make_logobj(), d, N=n_loc, rank=r, world=world, N_global=N, chain_offset=off, device=r, **rank_kw, **kw)
             s.set_archive(Z0)
             s.comm_init(uid)
             infos[r] = s.peer_info()
             bar.wait(60)
             s.open_peers(b"".join(infos))
             bar.wait(60)
-            s.run(G // 2)
+            for c in chunks:
+                s.run(c)
             info = s.run()
             X, lp = s.get_state()
-            out[r] = (X, lp, s.get_archive(), info)
+            out[r] = (X, lp, s.get_archive(), info, s.get_archive_checksum())
             bar.wait(60)
             s.close()
         except Exception as e:  # noqa: BLE001
@@ -142,11 +118,66 @@ def test_two_gpus_exchange_layouts_bitwise(d, sync_mode, layout, fused, monkeypa
     for t in th:
         t.join(300)
     assert not err, err
+    return out
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("d,sync_mode,layout,engine", [
+    (10, "strict", "in_place", "kernel"), (10, "overlap", "in_place", "copy_engine"), (13, "overlap", "in_place", "kernel"),
+    (20, "strict", "dense_slots", "kernel"), (20, "overlap", "dense_slots", "kernel"), (20, "overlap", "dense_slots", "copy_engine"),
+    (20, "strict", "dense_slots", "copy_engine"), (20, "overlap", "in_place", "copy_engine"), (20, "overlap", "in_place", "kernel")])
+def test_two_gpus_exchange_layouts_bitwise(d, sync_mode, layout, engine):
+    """The ways a rank's appended rows reach the peers' replicas — padded slots or an archive without slot padding
+    (dense_slots), moved by our push kernel or by the copy engines, the step kernels polling the segment flag words in
+    their prologue — all give the state / archive / accept counts of one GPU bit for bit.  Two run calls, so that the
+    drain between them is exercised."""
+    N, K, G = 512, 3, 36
+    S = 0.3 * np.ones((d, d)) + 0.7 * np.eye(d)
+    mu = np.linspace(-1, 1, d)
+    Z0 = np.random.default_rng(d).normal(size=(2 * N, d))
+    kw = dict(K=K, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.38, seed=11,
+              store_chain=False, sync_mode=sync_mode)
+    if (d, sync_mode) not in _one_gpu_cache:
+        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, device=0, **kw) as s:
+            s.set_archive(Z0)
+            s.run(G // 2)
+            info1 = s.run()
+            _one_gpu_cache[(d, sync_mode)] = (s.get_state(), s.get_archive(), info1["accepted"], s.get_archive_checksum())
+    (X1, lp1), Z1, acc1, h1 = _one_gpu_cache[(d, sync_mode)]
+    out = _two_rank_run(lambda: DEMC.MvNormalLogpdf(mu, S), d, Z0, N, kw, [G // 2], exchange_layout=layout, push_engine=engine)
     np.testing.assert_array_equal(np.concatenate([o[0] for o in out]), X1)
     np.testing.assert_array_equal(np.concatenate([o[1] for o in out]), lp1)
     for o in out:
         np.testing.assert_array_equal(o[2], Z1)
+        assert o[4] == h1                                  # the device-side checksum agrees with the row-by-row comparison
     assert sum(o[3]["accepted"] for o in out) == acc1
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("sync_mode,layout,blocks", [("overlap", "in_place", 1), ("overlap", "dense_slots", 1), ("strict", "in_place", 1),
+                                                     ("overlap", "in_place", 2)])
+def test_two_gpus_ring_wrap_bitwise(sync_mode, layout, blocks):
+    """The archive ring wraps several times during the run.  In overlap mode a peer may push its NEXT segment into this
+    replica while this rank is still drawing, so the view keeps off the 2 N oldest rows (demcz_archive_view) — for every
+    world size, hence still bit-identical to one GPU."""
+    d, N, K, G = 20, 512, 2, 60
+    S = 0.3 * np.ones((d, d)) + 0.7 * np.eye(d)
+    mu = np.linspace(-1, 1, d)
+    Z0 = np.random.default_rng(5).normal(size=(2 * N, d))
+    bi = [list(range(d))] if blocks == 1 else [list(range(0, 7)), list(range(7, d))]
+    kw = dict(K=K, Ngeneration=G, blockindex=bi, eps_scale=1e-5 * np.ones(d), γ=2.38, seed=13,
+              store_chain=False, sync_mode=sync_mode, archive_capacity=6 * N)          # 30 appends into a 6-segment ring
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, device=0, **kw) as s:
+        s.set_archive(Z0)
+        info1 = s.run()
+        (X1, lp1), Z1 = s.get_state(), s.get_archive()
+    assert Z1.shape[0] == 6 * N
+    out = _two_rank_run(lambda: DEMC.MvNormalLogpdf(mu, S), d, Z0, N, kw, [], exchange_layout=layout)
+    np.testing.assert_array_equal(np.concatenate([o[0] for o in out]), X1)
+    np.testing.assert_array_equal(np.concatenate([o[1] for o in out]), lp1)
+    for o in out:
+        np.testing.assert_array_equal(o[2], Z1)
+    assert sum(o[3]["accepted"] for o in out) == info1["accepted"]
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
