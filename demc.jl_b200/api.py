@@ -252,6 +252,17 @@ class Sampler:
         self.generations_total = info.generations_total
         return {k: getattr(info, k) for k, _ in _lib.RunInfo._fields_}
 
+    def kernel_info(self):
+        """Which kernels this context runs (demcz_get_kernel_info) as a dict."""
+        buf = C.create_string_buffer(1024)
+        self.lib.demcz_get_kernel_info(self.ctx, buf, 1024)
+        out = {}
+        for kv in buf.value.decode().split(";"):
+            if "=" in kv:
+                k, v = kv.split("=", 1)
+                out[k] = int(v) if v.lstrip("-").isdigit() else v
+        return out
+
     def set_profile(self, on=True):
         self._check(self.lib.demcz_set_profile(self.ctx, int(bool(on))))
 

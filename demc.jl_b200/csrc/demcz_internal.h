@@ -94,6 +94,7 @@ struct demcz_ctx {
     int64_t vis_waited = 0;
     int push_engine = 0;                         // 0: our push kernel (SM stores over NVLink), 1: copy engines (one peer copy per rank) + flag kernel
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
+    bool persistent_ok = false;                  // small-N persistent launches in effect (opts.persistent)
 
     // opts.moments: streaming first / second moments of every generation of every chain (mean_cov_chain of the full
     // history without the history).  Sums of (x - mom_shift): d_mom = [S1: 64 doubles][S2: 64 x 64 doubles, row-major]
@@ -147,3 +148,4 @@ double* demcz_linreg_lp(demcz_ctx* c);           // [ldx] FP64 log-objective of 
 double* demcz_linreg_lphist(demcz_ctx* c);       // [G][N]
 unsigned long long demcz_linreg_launches(demcz_ctx* c);
 double demcz_linreg_profile_ms(demcz_ctx* c, long long* launches);
+std::string demcz_linreg_info(demcz_ctx* c);     // "linreg_kind=...;..." or ""

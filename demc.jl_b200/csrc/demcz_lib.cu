@@ -176,15 +176,15 @@ __global__ void state_moments_kernel(const float* __restrict__ X, int n, int ldx
     if (y < d * d) {
         const int k1 = y / d, k2 = y % d;
         if (k1 > k2) return;
-        const float s1 = shift[k1], s2 = shift[k2];
+        const double s1 = shift[k1], s2 = shift[k2];
         for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
-            s += (double)(X[(size_t)k1 * ldx + i] - s1) * (double)(X[(size_t)k2 * ldx + i] - s2);
+            s += ((double)X[(size_t)k1 * ldx + i] - s1) * ((double)X[(size_t)k2 * ldx + i] - s2);
         s = block_sum(s, sm);
         if (threadIdx.x == 0) atomicAdd(&mom[64 + k1 * 64 + k2], s);
     } else {
         const int k = y - d * d;
-        const float s1 = shift[k];
-        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (double)(X[(size_t)k * ldx + i] - s1);
+        const double s1 = shift[k];
+        for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) s += (double)X[(size_t)k * ldx + i] - s1;
         s = block_sum(s, sm);
         if (threadIdx.x == 0) atomicAdd(&mom[k], s);
     }
@@ -868,7 +868,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; memcpy(a.shift2, c->shift, sizeof a.shift2); }
 
             const bool full = o.Nblocks == 1 && a.blocks[0].mask == (o.d == 32 ? 0xFFFFFFFFu : ((1u << o.d) - 1u));
-            a.thin = c->thin;
+            a.thin = c->thin; a.hist_phase = (int)(g % c->thin); a.hist_idx0 = (unsigned int)(g / c->thin);
             a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank;
             a.need = demcz_comm_need(c);
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
@@ -955,6 +955,19 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         }
     }
     return DEMCZ_OK;
+}
+
+extern "C" int demcz_get_kernel_info(demcz_ctx* c, char* buf, int64_t len)
+{
+    if (!c) return DEMCZ_ERR_INVALID;
+    std::string s = demcz_linreg_info(c);
+    s += c->persistent_ok ? "step_persistent=1;" : "step_persistent=0;";
+    if (buf && len > 0) {
+        const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
+        memcpy(buf, s.data(), n);
+        buf[n] = 0;
+    }
+    return (int)s.size() + 1;
 }
 
 extern "C" int demcz_set_profile(demcz_ctx* c, int32_t on)

@@ -26,6 +26,7 @@
 #include "demcz_tcgen05.cuh"
 
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cmath>
 #include <cstring>
 #include <vector>
@@ -42,7 +43,7 @@ using namespace demcz;
 
 struct demcz_linreg_state {
     int64_t n = 0;
-    int p = 0, ppad = 0, ksteps = 0;
+    int p = 0, ppad = 0, ksteps = 0, ksteps16 = 0;  // K steps of 8 TF32 / 16 FP16 elements covering p
     float *Xhi = nullptr, *Xlo = nullptr;          // [n][ppad] row-major, TF32-rounded hi / lo parts
     double *d_b0 = nullptr, *d_g = nullptr;        // [64]
     double ssr0 = 0.0;
@@ -54,7 +55,19 @@ struct demcz_linreg_state {
     double* lphist64 = nullptr;                    // [G][N]
     uint32_t* wacc = nullptr;                      // [ldx] accept word of the pending proposal
     int tile_n = 0, tiles = 0, R = 0, tiles_per_chunk = 0;
-    int terms = 3;                                 // 3xTF32 (FP32-equivalent) or 1 (plain TF32; measurement only)
+    int terms = 3;                                 // 3 MMA terms per product (FP32-equivalent) or 1 (measurement only)
+    // kind 1 (default): 2-way FP16 split on tcgen05 kind::f16 — x = hi + lo, both FP16, operands pre-scaled by powers of
+    // two (one exponent per regressor column folded into X, its inverse into d; one exponent per chain for d), the
+    // same three products d_lo X_hi + d_hi X_lo + d_hi X_hi at twice the TF32 MMA rate and half the X bytes.
+    // kind 0: the 3xTF32 split (fallback when the FP16 path's self-test fails; DEMCZ_LINREG_KIND=tf32 forces it).
+    int kind = 1;
+    __half* Xh = nullptr;                          // [n][2 ppad] row-major: [hi(ppad) | lo(ppad)] of X[:,k] * 2^xexp[k]
+    uint32_t* Dh = nullptr;                        // [Npad][ppad] words: [hi pairs (ppad/2) | lo pairs (ppad/2)] of d * 2^(Dexp - xexp)
+    int* Dexp = nullptr;                           // [Npad] per-chain exponent
+    int xexp[64] = {0};                            // per-column exponent
+    int swap_halves = 0;                           // which half of a 32-bit TMEM column holds the even K element (probed)
+    std::string fallback_reason;                   // why kind 1 was not used (self-test message), if it was asked for
+    CUtensorMap tmXh;
     CUtensorMap tmXhi, tmXlo;
     int sms = 148;
     unsigned long long ssr_launches = 0;
@@ -82,6 +95,37 @@ __global__ void split_x_kernel(const double* __restrict__ X, long long n, int p,
         }
         hi[i * ppad + k] = h;
         lo[i * ppad + k] = l;
+    }
+}
+
+// column-wise max |X[:,k]| (as the bit pattern of a non-negative float: integer max == float max)
+__global__ void colabsmax_kernel(const double* __restrict__ X, long long n, int p, int* __restrict__ out)
+{
+    const int k = blockIdx.y;
+    float m = 0.f;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        m = fmaxf(m, fabsf((float)X[i + n * k]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out + k, __float_as_int(m));
+}
+
+// X col-major FP64 (n x p) -> row-major [n][2 ppad] FP16: [hi | lo] of X[:,k] * 2^xexp[k]  (|scaled| < 2^15)
+struct XExp { int e[64]; };
+__global__ void split_x_f16_kernel(const double* __restrict__ X, long long n, int p, int ppad, XExp xe, __half* __restrict__ out)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    __half* row = out + i * (2 * ppad);
+    for (int k = 0; k < ppad; ++k) {
+        __half h = __float2half_rn(0.f), l = h;
+        if (k < p) {
+            const double x = scalbn(X[i + n * k], xe.e[k]);
+            h = __float2half_rn((float)x);
+            l = __float2half_rn((float)(x - (double)__half2float(h)));
+        }
+        row[k] = h;
+        row[ppad + k] = l;
     }
 }
 
@@ -174,6 +218,8 @@ struct LinArgs {
     __device__ uint32_t group_mask(int k) const { return ((k < 32 ? mask_lo : mask_hi) >> (k & 24)) & 0xFFu; }   // 8-column jitter group of k
     // outputs of propose
     float* Xprop; uint32_t* wacc; float *Dhi, *Dlo; double* lin;
+    // FP16-split operands (kind 1): packed words + per-chain exponent; column exponents; TMEM half order
+    int kind; uint32_t* Dh; int* Dexp; int xexp[64]; int swap_halves;
     const double *b0, *g;
     // trace
     uint32_t *tr_r1, *tr_r2; float *tr_u, *tr_xprop;
@@ -214,6 +260,7 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
     // Arithmetic and summation order are those of a plain column loop.
     const int LD4 = (a.d + 3) & ~3;                 // floats of an archive row that exist (rows are 16-byte aligned)
     double lin = 0.0;
+    float dmax = 0.f;                               // kind 1: max_k |d_k| 2^-xexp[k]
     for (int k0 = 0; k0 < a.d; k0 += 8) {
         float x[8], dz[8];
 #pragma unroll
@@ -243,6 +290,10 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
             x[j] = xp;
             const double dd = (double)xp - (k < a.d ? a.b0[k] : 0.0);
             const float df = (float)dd;
+            if (a.kind == 1) {
+                if (k < a.d) dmax = fmaxf(dmax, fabsf(scalbnf(df, -a.xexp[k])));
+                continue;
+            }
             hi[j] = k < a.d ? tc::to_tf32(df) : 0.f;
             lo[j] = k < a.d ? tc::to_tf32(df - hi[j]) : 0.f;
             // the GEMM sees hi + lo; use the same value in the linear term
@@ -258,11 +309,46 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
                 }
             }
         }
+        if (a.kind == 1) continue;
         // operand rows are ppad (32 or 64) floats and zero beyond d: whole 16-byte stores
         float4* dh = reinterpret_cast<float4*>(a.Dhi + (size_t)chain * a.ppad + k0);
         float4* dl = reinterpret_cast<float4*>(a.Dlo + (size_t)chain * a.ppad + k0);
         dh[0] = make_float4(hi[0], hi[1], hi[2], hi[3]); dh[1] = make_float4(hi[4], hi[5], hi[6], hi[7]);
         dl[0] = make_float4(lo[0], lo[1], lo[2], lo[3]); dl[1] = make_float4(lo[4], lo[5], lo[6], lo[7]);
+    }
+    if (a.kind == 1) {
+        // ---- FP16 split: d''_k = d_k 2^(f - xexp[k]) with the per-chain exponent f such that max_k |d''_k| is in [2^14, 2^15)
+        // (exact power-of-two scalings), hi = fp16(d''), lo = fp16(d'' - hi): 22 significant bits for the large components,
+        // absolute error <= 2^-25 (FP16 subnormal spacing) for the small ones, i.e. <= 2^-39 of the largest
+        int f = 0;
+        if (dmax > 0.f) { int ex; frexpf(dmax, &ex); f = min(100, max(-100, 15 - ex)); }
+        const float* xsrc = propose ? a.Xprop : a.X;               // pass 1 left x' there (same thread: program order)
+        uint32_t* drow = a.Dh + (size_t)chain * a.ppad;
+        const int HW = a.ppad / 2;                                 // words of the hi part
+        for (int k0 = 0; k0 < a.ppad; k0 += 8) {
+            uint32_t wh[4], wl[4];
+#pragma unroll
+            for (int j = 0; j < 8; j += 2) {
+                unsigned short h16[2], l16[2];
+#pragma unroll
+                for (int t = 0; t < 2; ++t) {
+                    const int k = k0 + j + t;
+                    float v = 0.f;
+                    if (k < a.d) v = scalbnf((float)((double)xsrc[(size_t)k * a.ldx + chain] - a.b0[k]), f - a.xexp[k]);
+                    const __half h = __float2half_rn(v);
+                    const __half l = __float2half_rn(v - __half2float(h));
+                    h16[t] = __half_as_ushort(h); l16[t] = __half_as_ushort(l);
+                    // the GEMM sees hi + lo; use the same value in the linear term
+                    if (k < a.d) lin += scalbn((double)__half2float(h) + (double)__half2float(l), a.xexp[k] - f) * a.g[k];
+                }
+                const int e = a.swap_halves ? 1 : 0;               // which K element sits in the low half-word of a TMEM column
+                wh[j >> 1] = (uint32_t)h16[e] | ((uint32_t)h16[1 - e] << 16);
+                wl[j >> 1] = (uint32_t)l16[e] | ((uint32_t)l16[1 - e] << 16);
+            }
+            *reinterpret_cast<uint4*>(drow + (k0 >> 1)) = make_uint4(wh[0], wh[1], wh[2], wh[3]);
+            *reinterpret_cast<uint4*>(drow + HW + (k0 >> 1)) = make_uint4(wl[0], wl[1], wl[2], wl[3]);
+        }
+        a.Dexp[chain] = f;
     }
     a.lin[chain] = lin;
 }
@@ -570,6 +656,178 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------------------
+// the same contraction on kind::f16 with the 2-way FP16 split.  Per data row the B operand is ONE row of
+// [hi(PPAD) | lo(PPAD)] halves (4 PPAD bytes: PPAD/32 boxes of 128 bytes), the chain tile in TMEM is
+// [hi pairs | lo pairs] (PPAD 32-bit columns).  A K step is 16 halves = 32 bytes of the swizzled row = 8 TMEM columns,
+// so the descriptor arithmetic is that of the TF32 kernel; half as many MMAs and half the X bytes per product.
+// ------------------------------------------------------------------------------------------------
+template <int PPAD, int TILE_N, int STAGES>
+struct SsrSmemH {
+    static constexpr int KBB = PPAD / 32;                          // 128-byte boxes per data row: hi|lo of 32, or hi, lo of 64
+    static constexpr int STAGE_BYTES = KBB * TILE_N * 128;
+    static constexpr int BAR_OFF = STAGES * STAGE_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 256 + 1024;
+};
+
+// TMEM columns: [0, 2 TILE_N) two accumulator stages | d_hi (PPAD/2 columns) | d_lo (PPAD/2 columns)
+template <int PPAD, int TILE_N, int STAGES, int TERMS>
+__global__ void __launch_bounds__(kSsrThreads, 1)
+linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* __restrict__ Dh, const int* __restrict__ Dexp,
+                      int ksteps, int tiles, int tiles_per_chunk, int CT, int units, int npad, double* __restrict__ partial)
+{
+    using L = SsrSmemH<PPAD, TILE_N, STAGES>;
+    constexpr int KBB = L::KBB;
+    constexpr int ACC = 2;
+    constexpr uint32_t A_COL = ACC * TILE_N;
+    constexpr uint32_t TMEM_COLS = 512;
+    static_assert(A_COL + PPAD <= TMEM_COLS, "TMEM budget");
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* sB = smem;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L::BAR_OFF);
+    uint64_t* full = bars;
+    uint64_t* empty = bars + STAGES;
+    uint64_t* a_full = bars + 2 * STAGES;
+    uint64_t* tfull = a_full + 1;
+    uint64_t* tempty = tfull + ACC;
+    uint32_t* tmem_holder = reinterpret_cast<uint32_t*>(tempty + ACC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tc::tma_prefetch_desc(&tmXh);
+        for (int s = 0; s < STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        tc::mbar_init(a_full, kEpiWarps);
+        for (int s = 0; s < ACC; ++s) { tc::mbar_init(&tfull[s], 1); tc::mbar_init(&tempty[s], kEpiWarps); }
+        tc::fence_barrier_init();
+    }
+    if (warp == 1) tc::tmem_alloc(tmem_holder, TMEM_COLS);
+    tc::tc_fence_before();
+    __syncthreads();
+    tc::tc_fence_after();
+    const uint32_t tmem_base = *tmem_holder;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            int stage = 0; uint32_t ph = 0;
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int rc = u / CT;
+                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    tc::mbar_wait(&empty[stage], ph ^ 1);
+                    tc::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
+                    uint8_t* b = sB + stage * L::STAGE_BYTES;
+                    for (int kb = 0; kb < KBB; ++kb) tc::tma_load_2d(b + kb * TILE_N * 128, &tmXh, kb * 64, t * TILE_N, &full[stage]);
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            constexpr uint32_t idesc = tc::make_idesc_f16(128, TILE_N);
+            int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
+            const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + PPAD / 2;
+            // descriptor offset (16-byte units) of K step ks of the hi (part 0) / lo (part 1) half of a data row
+            auto boff = [](int part, int ks) -> uint64_t {
+                const int e = part * PPAD + ks * 16;                       // first half-element of the step inside the row
+                return (uint64_t)(((e >> 6) * TILE_N * 128 + (e & 63) * 2) >> 4);
+            };
+            for (int u = blockIdx.x; u < units; u += gridDim.x) {
+                const int rc = u / CT;
+                tc::mbar_wait(a_full, aph);
+                aph ^= 1;
+                tc::tc_fence_after();
+                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+                for (int t = t0; t < t1; ++t) {
+                    tc::mbar_wait(&tempty[as], tph ^ 1);
+                    tc::mbar_wait(&full[stage], ph);
+                    tc::tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
+                    const uint64_t b0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
+                    uint32_t accum = 0;
+                    if (TERMS == 3) {                                      // cross terms first
+                        for (int ks = 0; ks < ksteps; ++ks) {
+                            tc::mma_f16_ts(d_tmem, a_lo + ks * 8, b0 + boff(0, ks), idesc, accum); accum = 1;
+                            tc::mma_f16_ts(d_tmem, a_hi + ks * 8, b0 + boff(1, ks), idesc, accum);
+                        }
+                    }
+                    for (int ks = 0; ks < ksteps; ++ks) {
+                        tc::mma_f16_ts(d_tmem, a_hi + ks * 8, b0 + boff(0, ks), idesc, accum); accum = 1;
+                    }
+                    tc::mma_commit(&empty[stage]);
+                    tc::mma_commit(&tfull[as]);
+                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                    if (++as == ACC) { as = 0; tph ^= 1; }
+                }
+            }
+        }
+    } else {
+        // ===================== epilogue warps =====================
+        constexpr int HALVES = kEpiWarps / 4;
+        constexpr int COLS = TILE_N / HALVES;
+        static_assert(COLS % 32 == 0, "epilogue column split");
+        const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;
+        int as = 0; uint32_t tph = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT, ct = u - rc * CT;
+            const int chain = ct * 128 + quarter * 32 + lane;
+            {
+                // chain tile -> TMEM: PPAD words per chain, 32 columns per store; PPAD = 32: one store (first warp of the
+                // quarter), PPAD = 64: hi words by one warp, lo words by the other
+                if (half < PPAD / 32) {
+                    const uint32_t* src = Dh + (size_t)chain * PPAD + half * 32;
+                    uint32_t v[32];
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        const uint4 t4 = *reinterpret_cast<const uint4*>(src + j);
+                        v[j] = t4.x; v[j + 1] = t4.y; v[j + 2] = t4.z; v[j + 3] = t4.w;
+                    }
+                    tc::tmem_st32(tmem_base + ((uint32_t)(quarter * 32) << 16) + A_COL + half * 32, v);
+                    tc::tmem_st_wait();
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(a_full);
+            }
+            const int fexp = Dexp[chain];
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            double accd = 0.0;
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&tfull[as], tph);
+                tc::tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TILE_N + half * COLS);
+                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+                for (int c = 0; c < COLS; c += 32) {
+                    float v[32];
+                    tc::tmem_ld32(taddr + c, v);
+                    tc::tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) {
+                        s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
+                        s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
+                    }
+                }
+                tc::tc_fence_before();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&tempty[as]);
+                accd += (double)((s0 + s1) + (s2 + s3));
+                if (++as == ACC) { as = 0; tph ^= 1; }
+            }
+            // undo the chain's power-of-two scale (the accumulators hold (2^f x.d)^2 sums)
+            partial[(size_t)(rc * HALVES + half) * npad + chain] = scalbn(accd, -2 * fexp);
+        }
+    }
+
+    tc::tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tc::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+// ------------------------------------------------------------------------------------------------
 // host helpers
 // ------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -604,6 +862,54 @@ int make_map(demcz_ctx* c, CUtensorMap* m, const float* base, uint64_t rows, int
     return DEMCZ_OK;
 }
 
+// row-major FP16 [rows][2 ppad] -> boxes of [box_rows][64 halves = 128 B], 128-byte swizzle, OOB rows read as zero
+int make_map_f16(demcz_ctx* c, CUtensorMap* m, const __half* base, uint64_t rows, int ppad, int box_rows)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return demcz_fail(c, DEMCZ_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const cuuint64_t dims[2] = {(cuuint64_t)(2 * ppad), (cuuint64_t)rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)(2 * ppad) * sizeof(__half)};
+    const cuuint32_t box[2] = {64u, (cuuint32_t)box_rows};
+    const cuuint32_t estr[2] = {1u, 1u};
+    const CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return demcz_fail(c, DEMCZ_ERR_CUDA, "cuTensorMapEncodeTiled (FP16) failed with CUresult %d", (int)r);
+    return DEMCZ_OK;
+}
+
+template <int PPAD, int TILE_N, int STAGES, int TERMS>
+cudaError_t launch_ssr_f16_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
+                             int tiles_per_chunk, int R, int CT, int npad, double* partial)
+{
+    auto kern = linreg_ssr_f16_kernel<PPAD, TILE_N, STAGES, TERMS>;
+    constexpr int smem = SsrSmemH<PPAD, TILE_N, STAGES>::TOTAL;
+    static bool configured[64] = {false};
+    const int dev = c->device & 63;
+    if (!configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    const int units = CT * R;
+    const int grid = std::min(units, s->sms);
+    kern<<<grid, kSsrThreads, smem, c->stream>>>(tm, dh, dexp, s->ksteps16, tiles, tiles_per_chunk, CT, units, npad, partial);
+    return cudaGetLastError();
+}
+
+constexpr int kTileNH = 192;          // data rows per MMA of the FP16 kernel: 2 N + PPAD <= 512 TMEM columns for PPAD = 32 and 64
+
+cudaError_t launch_ssr_f16(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
+                           int tiles_per_chunk, int R, int CT, int npad, double* partial)
+{
+    if (s->ppad == 32) {
+        if (s->terms == 3) return launch_ssr_f16_t<32, kTileNH, 6, 3>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+        return launch_ssr_f16_t<32, kTileNH, 6, 1>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+    }
+    if (s->terms == 3) return launch_ssr_f16_t<64, kTileNH, 4, 3>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+    return launch_ssr_f16_t<64, kTileNH, 4, 1>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+}
+
 template <int KB, int TILE_N, int STAGES, int TERMS>
 cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial)
 {
@@ -625,8 +931,11 @@ cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, 
 
 constexpr int kTileN32 = 192, kTileN64 = 128;     // data rows per MMA (N) for p <= 32 / p <= 64: 2 N + chain-tile columns <= 512 TMEM columns
 
-cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial)
+cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial,
+                       const uint32_t* dh = nullptr, const int* dexp = nullptr)
 {
+    if (s->kind == 1)
+        return launch_ssr_f16(c, s, s->tmXh, dh ? dh : s->Dh, dexp ? dexp : s->Dexp, s->tiles, s->tiles_per_chunk, s->R, CT, npad, partial);
     if (s->ppad == 32) {
         if (s->terms == 3) return launch_ssr_t<1, kTileN32, 4, 3>(c, s, dhi, dlo, CT, npad, partial);
         return launch_ssr_t<1, kTileN32, 4, 1>(c, s, dhi, dlo, CT, npad, partial);
@@ -646,11 +955,82 @@ void demcz_linreg_free(demcz_ctx* c)
 {
     demcz_linreg_state* s = c->linreg;
     if (!s) return;
-    void* ptrs[] = {s->Xhi, s->Xlo, s->d_b0, s->d_g, s->Dhi, s->Dlo, s->Xprop, s->lin, s->partial, s->lp64, s->lphist64, s->wacc};
+    void* ptrs[] = {s->Xhi, s->Xlo, s->d_b0, s->d_g, s->Dhi, s->Dlo, s->Xprop, s->lin, s->partial, s->lp64, s->lphist64, s->wacc,
+                    s->Xh, s->Dh, s->Dexp};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
     c->linreg = nullptr;
+}
+
+static int linreg_register(demcz_ctx* c, demcz_linreg_state* s, int64_t n, int32_t p, const double* X, const double* y);
+
+static void linreg_init_geometry(demcz_linreg_state* s, int64_t n, int32_t p)
+{
+    s->n = n; s->p = p; s->ppad = p <= 32 ? 32 : 64; s->ksteps = (p + 7) / 8; s->ksteps16 = (p + 15) / 16;
+}
+
+// One launch of the FP16 kernel on a hand-made tile whose result tells how the hardware reads the packed FP16 chain
+// tile from tensor memory: the even K element of a pair in the low half-word of the 32-bit column (swap_halves = 0) or
+// in the high one (1).  Anything else -> DEMCZ_ERR_UNSUPPORTED and the caller falls back to the 3xTF32 kernel.
+static int linreg_f16_selftest(demcz_ctx* c, demcz_linreg_state* s)
+{
+    const int ppad = s->ppad, W = 2 * ppad, TN = kTileNH;
+    std::vector<__half> hx((size_t)TN * W, __float2half(0.f));
+    auto setx = [&](int col, float v) { for (int r = 0; r < TN; ++r) hx[(size_t)r * W + col] = __float2half(v); };
+    setx(0, 1.f); setx(1, 2.f); setx(16, 3.f); setx(17, 5.f);
+    if (ppad == 64) { setx(32, 7.f); setx(33, 13.f); setx(48, 11.f); setx(49, 17.f); }
+    setx(ppad + 0, 0.5f);                                           // X_lo[:, 0]
+    std::vector<uint32_t> hd((size_t)128 * ppad, 0u);
+    std::vector<int> hexp(128, 0);
+    auto one = [](float v) { return (uint32_t)__half_as_ushort(__float2half(v)); };
+    const int HW = ppad / 2;
+    hd[0 * ppad + 0] = one(1.f);                                    // chain 0: d_hi[0] = 1
+    hd[1 * ppad + 8] = one(1.f);                                    // chain 1: d_hi[16] = 1 (second K step)
+    hd[2 * ppad + HW + 0] = one(1.f);                               // chain 2: d_lo[0] = 1
+    hd[3 * ppad + 0] = one(4.f); hexp[3] = 2;                       // chain 3: d_hi[0] = 4 at chain exponent 2
+    if (ppad == 64) { hd[4 * ppad + 16] = one(1.f); hd[5 * ppad + 24] = one(1.f); }     // d_hi[32], d_hi[48]
+    const double nat[6] = {2.25, 9.0, 1.0, 2.25, 49.0, 121.0}, swp[6] = {4.0, 25.0, 4.0, 4.0, 169.0, 289.0};
+    const int ncheck = ppad == 64 ? 6 : 4;
+
+    __half* dx = nullptr; uint32_t* dd = nullptr; int* de = nullptr; double* dp = nullptr;
+    CUL(c, cudaMalloc((void**)&dx, hx.size() * sizeof(__half)));
+    cudaError_t e = cudaMalloc((void**)&dd, hd.size() * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&de, 128 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&dp, 2 * 128 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dx, hx.data(), hx.size() * sizeof(__half), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dd, hd.data(), hd.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(de, hexp.data(), 128 * sizeof(int), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dp, 0, 2 * 128 * sizeof(double), c->stream);
+    int rc = DEMCZ_OK;
+    CUtensorMap tm;
+    if (e == cudaSuccess) rc = make_map_f16(c, &tm, dx, (uint64_t)TN, ppad, TN);
+    double hp[256] = {0};
+    if (e == cudaSuccess && rc == DEMCZ_OK) {
+        const int ks_save = s->ksteps16;
+        s->ksteps16 = ppad / 16;
+        e = launch_ssr_f16(c, s, tm, dd, de, 1, 1, 1, 1, 128, dp);
+        s->ksteps16 = ks_save;
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hp, dp, sizeof hp, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    }
+    cudaFree(dx); if (dd) cudaFree(dd); if (de) cudaFree(de); if (dp) cudaFree(dp);
+    if (rc != DEMCZ_OK) return rc;
+    CUL(c, e);
+    bool is_nat = true, is_swp = true;
+    char got[256]; int off = 0;
+    for (int i = 0; i < ncheck; ++i) {
+        const double v = (hp[i] + hp[128 + i]) / TN;              // two column halves of the tile, TN identical rows
+        off += snprintf(got + off, sizeof got - off, " %.4g", v);
+        if (fabs(v - nat[i]) > 1e-6 * nat[i]) is_nat = false;
+        if (fabs(v - swp[i]) > 1e-6 * swp[i]) is_swp = false;
+    }
+    if (const char* dbg = getenv("DEMCZ_DEBUG")) if (atoi(dbg)) fprintf(stderr, "demcz: FP16 TMEM layout self-test:%s (natural %d, swapped %d)\n", got, is_nat, is_swp);
+    if (is_nat) { s->swap_halves = 0; return DEMCZ_OK; }
+    if (is_swp) { s->swap_halves = 1; return DEMCZ_OK; }
+    demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "FP16 tensor-memory operand self-test failed (per-row sums:%s); using the 3xTF32 kernel", got);
+    c->sticky = 0;
+    return DEMCZ_ERR_UNSUPPORTED;
 }
 
 extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y)
@@ -667,9 +1047,16 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     demcz_linreg_free(c);
     demcz_linreg_state* s = new demcz_linreg_state();
     c->linreg = s;
+    linreg_init_geometry(s, n, p);
+    if (const char* kd = getenv("DEMCZ_LINREG_KIND")) s->kind = (strcmp(kd, "tf32") == 0) ? 0 : 1;
+    return linreg_register(c, s, n, p, X, y);
+}
+
+// (re-)builds everything that depends on the MMA kind; called again with kind 0 if the FP16 self-test fails
+static int linreg_register(demcz_ctx* c, demcz_linreg_state* s, int64_t n, int32_t p, const double* X, const double* y)
+{
     const demcz_opts& o = c->o;
-    s->n = n; s->p = p; s->ppad = p <= 32 ? 32 : 64; s->ksteps = (p + 7) / 8;
-    s->tile_n = s->ppad == 32 ? kTileN32 : kTileN64;
+    s->tile_n = s->kind == 1 ? kTileNH : (s->ppad == 32 ? kTileN32 : kTileN64);
     s->tiles = (int)((n + s->tile_n - 1) / s->tile_n);
     s->R = std::max(1, std::min(37, s->tiles / 8));                 // row chunks: 37 | 148 keeps (chain tiles x chunks) balanced over the SMs
     s->tiles_per_chunk = (s->tiles + s->R - 1) / s->R;
@@ -680,19 +1067,29 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
 
     const size_t np = (size_t)n * s->ppad;
     double *dX = nullptr, *dy = nullptr, *dscr = nullptr;
-    CUL(c, cudaMalloc((void**)&s->Xhi, np * sizeof(float)));
-    CUL(c, cudaMalloc((void**)&s->Xlo, np * sizeof(float)));
+    if (s->kind == 1) {
+        CUL(c, cudaMalloc((void**)&s->Xh, 2 * np * sizeof(__half)));
+        CUL(c, cudaMalloc((void**)&s->Dh, (size_t)s->Npad * s->ppad * sizeof(uint32_t)));
+        CUL(c, cudaMalloc((void**)&s->Dexp, (size_t)s->Npad * sizeof(int)));
+        CUL(c, cudaMemsetAsync(s->Dh, 0, (size_t)s->Npad * s->ppad * sizeof(uint32_t), c->stream));
+        CUL(c, cudaMemsetAsync(s->Dexp, 0, (size_t)s->Npad * sizeof(int), c->stream));
+    } else {
+        CUL(c, cudaMalloc((void**)&s->Xhi, np * sizeof(float)));
+        CUL(c, cudaMalloc((void**)&s->Xlo, np * sizeof(float)));
+    }
     CUL(c, cudaMalloc((void**)&s->d_b0, 64 * sizeof(double)));
     CUL(c, cudaMalloc((void**)&s->d_g, 64 * sizeof(double)));
-    CUL(c, cudaMalloc((void**)&s->Dhi, (size_t)s->Npad * s->ppad * sizeof(float)));
-    CUL(c, cudaMalloc((void**)&s->Dlo, (size_t)s->Npad * s->ppad * sizeof(float)));
+    if (s->kind == 0) {
+        CUL(c, cudaMalloc((void**)&s->Dhi, (size_t)s->Npad * s->ppad * sizeof(float)));
+        CUL(c, cudaMalloc((void**)&s->Dlo, (size_t)s->Npad * s->ppad * sizeof(float)));
+        CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
+        CUL(c, cudaMemsetAsync(s->Dlo, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
+    }
     CUL(c, cudaMalloc((void**)&s->Xprop, (size_t)c->ldx * o.d * sizeof(float)));
     CUL(c, cudaMalloc((void**)&s->lin, (size_t)s->Npad * sizeof(double)));
     CUL(c, cudaMalloc((void**)&s->partial, (size_t)s->R * (kEpiWarps / 4) * s->Npad * sizeof(double)));
     CUL(c, cudaMalloc((void**)&s->lp64, (size_t)c->ldx * 2 * sizeof(double)));      // [lp | lp at generation start]
     CUL(c, cudaMalloc((void**)&s->wacc, (size_t)c->ldx * sizeof(uint32_t)));
-    CUL(c, cudaMemsetAsync(s->Dhi, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
-    CUL(c, cudaMemsetAsync(s->Dlo, 0, (size_t)s->Npad * s->ppad * sizeof(float), c->stream));
     CUL(c, cudaMemsetAsync(s->lp64, 0, (size_t)c->ldx * 2 * sizeof(double), c->stream));
     if (o.store_chain == 1 && o.Ngeneration / c->thin > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)(o.Ngeneration / c->thin) * o.N * sizeof(double)));
 
@@ -708,8 +1105,31 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     if (e == cudaSuccess) e = cudaMemcpyAsync(dX, X, (size_t)n * p * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     if (e == cudaSuccess) e = cudaMemcpyAsync(dy, y, (size_t)n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
     std::vector<double> hbuf(scr), G((size_t)npairs, 0.0);
+    if (e == cudaSuccess && s->kind == 1) {
+        // one power-of-two exponent per regressor column: max |X[:,k]| 2^xexp[k] in [2^14, 2^15)
+        int* dmax = reinterpret_cast<int*>(dscr);
+        e = cudaMemsetAsync(dmax, 0, 64 * sizeof(int), c->stream);
+        if (e == cudaSuccess) {
+            colabsmax_kernel<<<dim3(std::min(grid1(n), 592), p), 256, 0, c->stream>>>(dX, n, p, dmax);
+            e = cudaGetLastError();
+        }
+        int hmax[64] = {0};
+        if (e == cudaSuccess) e = cudaMemcpyAsync(hmax, dmax, (size_t)p * sizeof(int), cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        XExp xe;
+        for (int k = 0; k < 64; ++k) {
+            float m; memcpy(&m, &hmax[k], sizeof m);
+            int ex = 0;
+            if (k < p && m > 0.f && std::isfinite(m)) frexpf(m, &ex); else ex = 15;
+            s->xexp[k] = xe.e[k] = 15 - ex;
+        }
+        if (e == cudaSuccess) {
+            split_x_f16_kernel<<<grid1(n), 256, 0, c->stream>>>(dX, n, p, s->ppad, xe, s->Xh);
+            e = cudaGetLastError();
+        }
+    }
     if (e == cudaSuccess) {
-        split_x_kernel<<<grid1(n), 256, 0, c->stream>>>(dX, n, p, s->ppad, s->Xhi, s->Xlo);
+        if (s->kind == 0) split_x_kernel<<<grid1(n), 256, 0, c->stream>>>(dX, n, p, s->ppad, s->Xhi, s->Xlo);
         gram_kernel<<<gblocks, 256, 32 * P1 * sizeof(double), c->stream>>>(dX, dy, n, p, rpb, dscr);
         e = cudaGetLastError();
     }
@@ -771,8 +1191,25 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     if (dscr) cudaFree(dscr);
     CUL(c, e);
 
-    int rc = make_map(c, &s->tmXhi, s->Xhi, (uint64_t)n, s->ppad, s->tile_n);
-    if (rc == DEMCZ_OK) rc = make_map(c, &s->tmXlo, s->Xlo, (uint64_t)n, s->ppad, s->tile_n);
+    int rc = DEMCZ_OK;
+    if (s->kind == 1) {
+        rc = make_map_f16(c, &s->tmXh, s->Xh, (uint64_t)n, s->ppad, s->tile_n);
+        if (rc == DEMCZ_OK) rc = linreg_f16_selftest(c, s);
+        if (rc == DEMCZ_ERR_UNSUPPORTED) {
+            // the FP16 operand layout this library assumes is not what the hardware reads: use the 3xTF32 kernel
+            const std::string why = c->err;
+            demcz_linreg_free(c);
+            demcz_linreg_state* s2 = new demcz_linreg_state();
+            c->linreg = s2;
+            linreg_init_geometry(s2, n, p);
+            s2->kind = 0;
+            s2->fallback_reason = why;
+            return linreg_register(c, s2, n, p, X, y);
+        }
+    } else {
+        rc = make_map(c, &s->tmXhi, s->Xhi, (uint64_t)n, s->ppad, s->tile_n);
+        if (rc == DEMCZ_OK) rc = make_map(c, &s->tmXlo, s->Xlo, (uint64_t)n, s->ppad, s->tile_n);
+    }
     if (rc != DEMCZ_OK) return rc;
     c->lik_kind = DEMCZ_LIK_LINREG;
     c->state_lp_valid = false;
@@ -789,6 +1226,7 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
     const bool own_state = (out_dev == nullptr);           // the context's own chains -> lp64
     const int npad = (n + 127) / 128 * 128;
     float *dhi = s->Dhi, *dlo = s->Dlo; double *lin = s->lin, *partial = s->partial;
+    uint32_t* dh = s->Dh; int* dexp = s->Dexp;
     void* tmp = nullptr;
     if (npad > s->Npad) {                                   // evaluation of more points than chains: temporaries
         const size_t fb = (size_t)npad * s->ppad * sizeof(float);
@@ -796,16 +1234,18 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
         CUL(c, cudaMalloc(&tmp, total));
         CUL(c, cudaMemsetAsync(tmp, 0, total, c->stream));
         dhi = (float*)tmp; dlo = (float*)((char*)tmp + fb);
+        dh = (uint32_t*)tmp; dexp = (int*)((char*)tmp + fb);       // FP16 kind: packed words + exponents in the same space
         lin = (double*)((char*)tmp + 2 * fb); partial = lin + npad;
     }
     LinArgs a;
     memset(&a, 0, sizeof a);
     a.X = const_cast<float*>(X); a.N = n; a.ldx = ldx; a.d = c->o.d; a.ppad = s->ppad;
     a.Dhi = dhi; a.Dlo = dlo; a.lin = lin; a.b0 = s->d_b0; a.g = s->d_g;
+    a.kind = s->kind; a.Dh = dh; a.Dexp = dexp; memcpy(a.xexp, s->xexp, sizeof a.xexp); a.swap_halves = s->swap_halves;
     linreg_prepare_kernel<<<grid1(n, 128), 128, 0, c->stream>>>(a, false);
     cudaError_t e = cudaGetLastError();
     const int use_npad = npad > s->Npad ? npad : s->Npad;
-    if (e == cudaSuccess) e = launch_ssr(c, s, dhi, dlo, npad / 128, use_npad, partial);
+    if (e == cudaSuccess) e = launch_ssr(c, s, dhi, dlo, npad / 128, use_npad, partial, dh, dexp);
     if (e == cudaSuccess) {
         linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R * (kEpiWarps / 4), s->ssr0, own_state ? s->lp64 : out_dev);
         e = cudaGetLastError();
@@ -819,6 +1259,20 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
 double* demcz_linreg_lp(demcz_ctx* c) { return c->linreg ? c->linreg->lp64 : nullptr; }
 double* demcz_linreg_lphist(demcz_ctx* c) { return c->linreg ? c->linreg->lphist64 : nullptr; }
 unsigned long long demcz_linreg_launches(demcz_ctx* c) { return c->linreg ? c->linreg->ssr_launches : 0; }
+
+std::string demcz_linreg_info(demcz_ctx* c)
+{
+    demcz_linreg_state* s = c->linreg;
+    if (!s) return "";
+    char buf[512];
+    if (s->kind == 1)
+        snprintf(buf, sizeof buf, "linreg_kind=f16;linreg_terms=%d;linreg_kernel=linreg_ssr_f16_kernel<%d,%d> (tcgen05 kind::f16, 2-way FP16 split: %d MMA terms, A in TMEM%s);",
+                 s->terms, s->ppad, kTileNH, s->terms, s->swap_halves ? ", swapped halves" : "");
+    else
+        snprintf(buf, sizeof buf, "linreg_kind=tf32;linreg_terms=%d;linreg_kernel=linreg_ssr_kernel<%d,%d> (tcgen05 kind::tf32, 3xTF32 split, A in TMEM);linreg_fallback=%s;",
+                 s->terms, s->ppad / 32, s->tile_n, s->fallback_reason.c_str());
+    return buf;
+}
 
 double demcz_linreg_profile_ms(demcz_ctx* c, long long* launches)
 {
@@ -867,6 +1321,7 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             a.cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
             for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
             a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
+            a.kind = s->kind; a.Dh = s->Dh; a.Dexp = s->Dexp; memcpy(a.xexp, s->xexp, sizeof a.xexp); a.swap_halves = s->swap_halves;
             a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
             a.flags = demcz_flags(c); a.world = o.world; a.my_rank = o.rank;
             a.need = (gi == 0 && b == 0) ? demcz_comm_need(c) : 0ull;          // once per archive view

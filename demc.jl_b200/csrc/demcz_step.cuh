@@ -74,8 +74,10 @@ struct StepArgs {
     float* S1;                   // [d][ldx]  sum_t (x - shift)
     double* S2;                  // [d]       sum_chains sum_t (x - shift)^2
     float2 shift2[16];           // population mean at the start of the window (conditioning only), column pairs
-    // history thinning: generation grel is stored iff grel % thin == 0, at index grel / thin - 1 (thin >= 1)
-    int thin;
+    // history thinning: generation grel is stored iff grel % thin == 0, at index grel / thin - 1 (thin >= 1).
+    // hist_phase = (grel0 - 1) % thin, hist_idx0 = (grel0 - 1) / thin: computed by the host, the kernel only counts
+    int thin, hist_phase;
+    unsigned int hist_idx0;
     // multi-GPU: the segment flag words of THIS rank's archive allocation (written by the peers) and how many
     // segments must have landed from every peer before this launch may gather (0: nothing to wait for)
     const unsigned long long* flags;
@@ -421,12 +423,15 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             const bool changed = active && (lp != lp_gen0);
             cnt_run += (changed && cg != a.run_skip_gi) ? 1 : 0;
             cnt_win += (changed && cg != a.win_skip_gi) ? 1 : 0;
-            if (a.hist && active && (a.thin <= 1 || grel % a.thin == 0)) {
-                const size_t hi = (size_t)(a.thin <= 1 ? grel : grel / a.thin) - 1;      // thinned history index
+            if (a.hist) {                        // thinned history: generation t (counted from the last stored one) is kept iff t % thin == 0
+                const int t = a.hist_phase + cg + 1;
+                if (active && t % a.thin == 0) {
+                    const size_t hi = (size_t)a.hist_idx0 + (size_t)(t / a.thin) - 1;
 #pragma unroll
-                for (int k = 0; k < LD; ++k)
-                    if (k < a.d) a.hist[(hi * a.d + k) * a.N + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
-                a.lphist[hi * a.N + chain] = lp;
+                    for (int k = 0; k < LD; ++k)
+                        if (k < a.d) a.hist[(hi * a.d + k) * a.N + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
+                    a.lphist[hi * a.N + chain] = lp;
+                }
             }
             if (ACC) {
 #pragma unroll

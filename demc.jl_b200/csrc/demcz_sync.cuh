@@ -17,18 +17,19 @@ constexpr unsigned long long kSpinTimeoutNs = 20ull * 1000ull * 1000ull * 1000ul
 
 // Segment flags: peer r publishes `seq` into word [r] of THIS rank's flag block (st.release.sys after a system-scope
 // fence over its row stores) once its rows of segments 0 .. seq-1 have landed here.  Wait until word `f` >= need.
-// Normally zero spins: the segment a launch needs was pushed one K-block earlier (overlap sync mode).
+// Normally zero spins: the segment a launch needs was pushed one K-block earlier (overlap sync mode).  Bounded by wall
+// time through the sleep: 2^26 polls of >= ~100 ns each are at least several seconds (a dead peer ends as a failed
+// launch, never as a hung GPU; a healthy but slow peer is waited for).  Kept tiny and inline: it runs in the prologue
+// of the step kernel, which sits exactly at its 128-register budget.
 __device__ __forceinline__ void flag_wait(const unsigned long long* f, unsigned long long need)
 {
     unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-    if (v >= need) return;
-    const unsigned long long t0 = global_timer_ns();
+    unsigned int spins = 0;
     for (;;) {
-        __nanosleep(100);
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
         if (v >= need) return;
-        if (global_timer_ns() - t0 > kSpinTimeoutNs) __trap();   // a peer never delivered
+        if (++spins == (1u << 26)) __trap();     // a peer never delivered
+        __nanosleep(200);
     }
 }
 

@@ -157,6 +157,10 @@ int demcz_set_temperature_table(demcz_ctx* ctx, const double* T, int64_t len);
  * (src/demcz.jl:30-56, 80-93, 167-203; src/demcz_anneal.jl:39-58, 67-80, 142-178).
  * Runs up to max_generations more generations (<=0: all remaining). Blocking. */
 int demcz_run(demcz_ctx* ctx, int64_t max_generations, demcz_run_info* info);
+/* which kernels this context runs, as "key=value;..." text (measurement / reporting; no reference counterpart):
+ * linreg_kind (f16 | tf32), linreg_terms, linreg_kernel, linreg_fallback (why the FP16 kind was not used), step_persistent.
+ * Returns the length needed (>= 0); writes at most len-1 characters + NUL. */
+int demcz_get_kernel_info(demcz_ctx* ctx, char* buf, int64_t len);
 /* measurement switch (no reference counterpart): 1 = bracket every step-kernel launch of later
  * demcz_run calls with CUDA events on the context's stream (demcz_run_info.step_kernel_ms). */
 int demcz_set_profile(demcz_ctx* ctx, int32_t on);

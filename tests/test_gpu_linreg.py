@@ -135,3 +135,66 @@ def test_linreg_streaming_rhat_and_par_entry_point():
     assert mc.chain.shape == (N, d, 2 * every) and mc.info["rhat_valid"]
     ref = orc.rhat_gelman(mc.chain[:, :, every:])
     np.testing.assert_allclose(mc.info["rhat"], ref, rtol=5e-4)
+
+
+# ---- the 2-way FP16 split on tcgen05 kind::f16 (default) and the 3xTF32 kernel it falls back to ---------------------
+def _ill_scaled(nobs, p, rng):
+    """Regressor scales spread over 6 decades, heavy-tailed rows (10^4 x outliers), intercept, a near-constant column."""
+    X = rng.normal(size=(nobs, p))
+    X[:, 0] = 1.0
+    X *= 10.0 ** np.linspace(-3, 3, p)[None, :]
+    out = rng.choice(nobs, size=max(nobs // 200, 3), replace=False)
+    X[out, 1:] *= 1e4
+    X[:, p - 1] = 5.0 + 1e-3 * rng.normal(size=nobs)
+    beta = (1 + rng.random(p)) / 10.0 ** np.linspace(-3, 3, p)
+    y = X @ beta + rng.normal(size=nobs)
+    return X, y
+
+
+@pytest.mark.parametrize("kind", ["f16", "tf32"])
+@pytest.mark.parametrize("nobs,p", [(4000, 12), (3000, 40), (2500, 64)])
+def test_split_kinds_on_ill_scaled_regressors(kind, nobs, p, monkeypatch):
+    """North-star accuracy on data chosen to hurt an FP16 / TF32 operand split: log-objective within 1e-5 relative of
+    FP64 for points at posterior scale, at the mode and far away; differences near the mode accurate in absolute terms;
+    a traced run replays with exact decisions outside the tolerance band."""
+    monkeypatch.setenv("DEMCZ_LINREG_KIND", kind)
+    rng = np.random.default_rng(100 + p)
+    X, y = _ill_scaled(nobs, p, rng)
+    lo, ref = DEMC.LinRegLoglik(X, y), orc.LinRegLik(X, y)
+    bols = np.linalg.lstsq(X, y, rcond=None)[0]
+    sd = np.sqrt(np.diag(np.linalg.inv(X.T @ X)))
+    B = np.concatenate([bols + sd * rng.normal(size=(200, p)), bols[None, :], bols + 30 * sd * rng.normal(size=(55, p)),
+                        bols * (1 + 0.5 * rng.normal(size=(44, p)))])
+    with _sampler(lo) as s:
+        assert s.kernel_info()["linreg_kind"] == kind
+        got = s.eval_logdensity(B)
+    want = ref.logdensity(B)
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel.max() < 1e-5, rel.max()
+    near = slice(0, 201)
+    assert np.max(np.abs((got[near] - got[200]) - (want[near] - want[200]))) < 5e-3
+    N = 96
+    Z0 = bols + 2 * sd * rng.normal(size=(3 * N, p))
+    st = check_run_against_oracle(lo, Z0, N=N, K=4, G=8, blocks=[list(range(p))], eps=1e-5 * sd, gamma=2.0, seed=3)
+    assert st["max_lp_relerr"] < 1e-5
+
+
+def test_fp16_split_equals_tf32_split_decisions():
+    """Both kernels run the same chain: with decisions exact outside the band and log-objectives equal to ~1e-6 relative,
+    a short free-running chain on well-separated proposals takes the same accept decisions under either MMA kind."""
+    import os
+    X, y, _ = example_linreg_data(2000, 15)
+    d = 16
+    bols = np.linalg.solve(X.T @ X, X.T @ y)
+    Z0 = bols + 0.05 * np.random.default_rng(9).normal(size=(200, d))
+    res = {}
+    for kind in ("f16", "tf32"):
+        os.environ["DEMCZ_LINREG_KIND"] = kind
+        try:
+            mc, _ = DEMC.demcz_sample(DEMC.LinRegLoglik(X, y), Z0, 64, 10, 20, 1, [list(range(d))], 1e-5 * np.ones(d), 2.0, verbose=False)
+        finally:
+            os.environ.pop("DEMCZ_LINREG_KIND", None)
+        res[kind] = mc
+    np.testing.assert_allclose(res["f16"].log_obj[:, 0], res["tf32"].log_obj[:, 0], rtol=2e-6)
+    agree = np.mean(np.all(res["f16"].chain[:, :, -1] == res["tf32"].chain[:, :, -1], axis=1))
+    assert agree > 0.9                                      # a near-tie may flip a chain; most chains are bit-identical

@@ -339,3 +339,85 @@ def test_dense_slot_archive_is_bit_identical_to_padded_slots(d, blocks):
     np.testing.assert_allclose(a[3], b[3], rtol=1e-6)      # FP64 atomics across CTAs: summation order varies run to run
     assert a[4] == b[4]
     np.testing.assert_array_equal(a[5], b[5])
+
+
+def _small_linreg(rng, n=900, d=6, rows=80):
+    X = np.ones((n, d)); X[:, 1:] = rng.normal(size=(n, d - 1)); y = X @ (1 + rng.random(d)) + rng.normal(size=n)
+    return DEMC.LinRegLoglik(X, y), np.linalg.solve(X.T @ X, X.T @ y) + 0.05 * rng.normal(size=(rows, d))
+
+
+@pytest.mark.parametrize("kind", ["mvn", "linreg"])
+@pytest.mark.parametrize("store", [True, "stream"])
+def test_thinned_history_is_every_thin_th_generation(kind, store):
+    # opts.thin: MC.chain keeps generation g iff g % thin == 0 -> N x d x floor(G/thin), identical to the
+    # corresponding slices of the full history; state, archive and counters unchanged
+    rng = np.random.default_rng(21)
+    if kind == "mvn":
+        d = 5
+        mu, S = example_normpdf_target(d)
+        lo, Z0 = DEMC.MvNormalLogpdf(mu, S), _z0(80, d)
+    else:
+        lo, Z0 = _small_linreg(rng)
+        d = 6
+    args = (40, 7, 38, 1, [list(range(d))], 1e-5 * np.ones(d), 2.2)
+    full, Zf = DEMC.demcz_sample(lo, Z0, *args, verbose=False, store_chain=True)
+    for thin in (3, 7, 50):
+        th, Zt = DEMC.demcz_sample(lo, Z0, *args, verbose=(thin == 3), print_step=5, store_chain=store, thin=thin)
+        assert th.chain.shape == (40, d, 38 // thin) and th.log_obj.shape == (40, 38 // thin)
+        np.testing.assert_array_equal(th.chain, full.chain[:, :, thin - 1::thin][:, :, :38 // thin])
+        np.testing.assert_array_equal(th.log_obj, full.log_obj[:, thin - 1::thin][:, :38 // thin])
+        np.testing.assert_array_equal(th.Xcurrent, full.Xcurrent)
+        np.testing.assert_array_equal(Zt, Zf)
+
+
+@pytest.mark.parametrize("kind", ["mvn", "linreg", "mvn_blocks"])
+def test_history_moments_equal_mean_cov_chain_of_the_stored_history(kind):
+    # opts.moments: flatten_chain + mean_cov_chain (src/utils.jl:22-32, 96-106) of EVERY generation from
+    # device accumulators, without MC.chain; checked against utils.mean_cov_chain on the stored history of the same run
+    rng = np.random.default_rng(22)
+    if kind == "linreg":
+        lo, Z0 = _small_linreg(rng, rows=300)
+        d, blocks = 6, [list(range(6))]
+    else:
+        d = 7
+        mu, S = example_normpdf_target(d)
+        lo, Z0 = DEMC.MvNormalLogpdf(mu, S), _z0(300, d, scale=0.3)
+        blocks = [list(range(d))] if kind == "mvn" else [[0, 2, 4], [1, 3, 5, 6]]
+    N, K, G = 200, 5, 60
+    with DEMC.Sampler(lo, d, N=N, K=K, Ngeneration=G, blockindex=blocks, eps_scale=1e-5 * np.ones(d), γ=2.0, seed=8,
+                      store_chain=True, moments=True) as s:
+        s.set_archive(Z0)
+        s.run(23)
+        s.run()
+        chain, _ = s.get_chain()
+        m, c, n = s.get_history_moments()
+    assert n == N * G
+    mref, cref = DEMC.mean_cov_chain(chain)
+    np.testing.assert_allclose(m, mref, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(c, cref, rtol=2e-5, atol=1e-9 * np.abs(cref).max())
+    # and the run itself is the run without the accumulators
+    with DEMC.Sampler(lo, d, N=N, K=K, Ngeneration=G, blockindex=blocks, eps_scale=1e-5 * np.ones(d), γ=2.0, seed=8,
+                      store_chain=True) as s:
+        s.set_archive(Z0)
+        s.run()
+        chain0, _ = s.get_chain()
+        with pytest.raises(_lib.DemczError):
+            s.get_history_moments()
+    np.testing.assert_array_equal(chain, chain0)
+
+
+def test_archive_checksum_tracks_the_rows():
+    d, N = 5, 64
+    mu, S = example_normpdf_target(d)
+    Z0 = _z0(128, d)
+    hs = []
+    for Z in (Z0, Z0.copy(), np.roll(Z0, 1, axis=0)):
+        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=4, Ngeneration=16, blockindex=[list(range(d))],
+                          eps_scale=1e-5 * np.ones(d), γ=2.38, seed=3, store_chain=False, archive_capacity=256) as s:
+            s.set_archive(Z)
+            h0 = s.get_archive_checksum()
+            s.run()                                         # 4 appends of 64 rows into a 256-row ring: wraps
+            hs.append((h0, s.get_archive_checksum(), s.get_archive_checksum(0, 64)))
+    assert hs[0] == hs[1]                                   # same rows, same order -> same checksum (before, after, partial)
+    assert hs[0][0] != hs[2][0]                             # position-sensitive
+    assert hs[0][0] != hs[0][1] and hs[0][1] != hs[0][2]
