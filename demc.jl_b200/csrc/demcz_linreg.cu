@@ -533,62 +533,68 @@ linreg_ssr_kernel(const __grid_constant__ CUtensorMap tmXhi, const __grid_consta
 
     if (warp == 0) {
         // ===================== TMA producer: streams the X tiles of all this CTA's units =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int rc = u / CT;
-                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    tc::mbar_wait(&empty[stage], ph ^ 1);
+        // (whole warp in the loop, one elected lane issues — see linreg_ssr_f16_kernel)
+        int stage = 0; uint32_t ph = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT;
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&empty[stage], ph ^ 1);
+                uint8_t* bh = sB + stage * L::STAGE_BYTES;
+                uint8_t* bl = bh + L::B_BYTES;
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
-                    uint8_t* bh = sB + stage * L::STAGE_BYTES;
-                    uint8_t* bl = bh + L::B_BYTES;
+#pragma unroll
                     for (int kb = 0; kb < KB; ++kb) {
                         tc::tma_load_2d(bh + kb * TILE_N * 128, &tmXhi, kb * 32, t * TILE_N, &full[stage]);
                         tc::tma_load_2d(bl + kb * TILE_N * 128, &tmXlo, kb * 32, t * TILE_N, &full[stage]);
                     }
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_tf32(128, TILE_N);
-            int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
-            const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + KB * 32;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int rc = u / CT;
-                tc::mbar_wait(a_full, aph);                    // the epilogue warps stored this unit's chain tile
-                aph ^= 1;
+        // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = tc::make_idesc_tf32(128, TILE_N);
+        int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
+        const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + KB * 32;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT;
+            tc::mbar_wait(a_full, aph);                        // the epilogue warps stored this unit's chain tile
+            aph ^= 1;
+            tc::tc_fence_after();
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&tempty[as], tph ^ 1);
+                tc::mbar_wait(&full[stage], ph);
                 tc::tc_fence_after();
-                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    tc::mbar_wait(&tempty[as], tph ^ 1);
-                    tc::mbar_wait(&full[stage], ph);
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
-                    const uint64_t b_hi0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
-                    const uint64_t b_lo0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES + L::B_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
+                const uint64_t b_hi0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
+                const uint64_t b_lo0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES + L::B_BYTES);
+                if (tc::elect_one()) {
                     uint32_t accum = 0;
                     // a k-step is 8 TF32: 8 TMEM columns of the chain tile, 32 bytes inside the 128-byte swizzle row of X
                     // (descriptor start address + 2); a k-block is the next [rows][128 B] panel.  Cross terms first.
                     if (TERMS == 3) {
+#pragma unroll 4
                         for (int ks = 0; ks < ksteps; ++ks) {
                             const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
                             tc::mma_tf32_ts(d_tmem, a_lo + ks * 8, b_hi0 + bo, idesc, accum); accum = 1;
                             tc::mma_tf32_ts(d_tmem, a_hi + ks * 8, b_lo0 + bo, idesc, accum);
                         }
                     }
+#pragma unroll 4
                     for (int ks = 0; ks < ksteps; ++ks) {
                         const uint64_t bo = (uint64_t)(((ks >> 2) * TILE_N * 128 + (ks & 3) * 32) >> 4);
                         tc::mma_tf32_ts(d_tmem, a_hi + ks * 8, b_hi0 + bo, idesc, accum); accum = 1;
                     }
                     tc::mma_commit(&empty[stage]);             // X tile consumed -> producer may refill
                     tc::mma_commit(&tfull[as]);                // accumulator ready -> epilogue
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
-                    if (++as == ACC) { as = 0; tph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                if (++as == ACC) { as = 0; tph ^= 1; }
             }
         }
     } else {
@@ -709,58 +715,67 @@ linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* 
 
     if (warp == 0) {
         // ===================== TMA producer =====================
-        if (lane == 0) {
-            int stage = 0; uint32_t ph = 0;
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int rc = u / CT;
-                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    tc::mbar_wait(&empty[stage], ph ^ 1);
+        // The WHOLE warp runs the loop (warp-uniform control flow and addresses, so the compiler keeps them in uniform
+        // registers); one elected lane issues.  A loop under `if (lane == 0)` instead makes ptxas wrap every TMA / MMA
+        // instruction in an ELECT ... BRA.U.ANY serialisation loop (~150 cycles per instruction: measured, the MMA
+        // issue rate — not the tensor pipe — bounded the kernel).
+        int stage = 0; uint32_t ph = 0;
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT;
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&empty[stage], ph ^ 1);
+                uint8_t* b = sB + stage * L::STAGE_BYTES;
+                if (tc::elect_one()) {
                     tc::mbar_arrive_expect_tx(&full[stage], L::STAGE_BYTES);
-                    uint8_t* b = sB + stage * L::STAGE_BYTES;
+#pragma unroll
                     for (int kb = 0; kb < KBB; ++kb) tc::tma_load_2d(b + kb * TILE_N * 128, &tmXh, kb * 64, t * TILE_N, &full[stage]);
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            constexpr uint32_t idesc = tc::make_idesc_f16(128, TILE_N);
-            int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
-            const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + PPAD / 2;
-            // descriptor offset (16-byte units) of K step ks of the hi (part 0) / lo (part 1) half of a data row
-            auto boff = [](int part, int ks) -> uint64_t {
-                const int e = part * PPAD + ks * 16;                       // first half-element of the step inside the row
-                return (uint64_t)(((e >> 6) * TILE_N * 128 + (e & 63) * 2) >> 4);
-            };
-            for (int u = blockIdx.x; u < units; u += gridDim.x) {
-                const int rc = u / CT;
-                tc::mbar_wait(a_full, aph);
-                aph ^= 1;
+        // ===================== MMA issuer (whole warp in the loop, one elected lane issues) =====================
+        constexpr uint32_t idesc = tc::make_idesc_f16(128, TILE_N);
+        int stage = 0, as = 0; uint32_t ph = 0, aph = 0, tph = 0;
+        const uint32_t a_hi = tmem_base + A_COL, a_lo = tmem_base + A_COL + PPAD / 2;
+        // descriptor offset (16-byte units) of K step ks of the hi (part 0) / lo (part 1) half of a data row
+        auto boff = [](int part, int ks) -> uint64_t {
+            const int e = part * PPAD + ks * 16;                           // first half-element of the step inside the row
+            return (uint64_t)(((e >> 6) * TILE_N * 128 + (e & 63) * 2) >> 4);
+        };
+        for (int u = blockIdx.x; u < units; u += gridDim.x) {
+            const int rc = u / CT;
+            tc::mbar_wait(a_full, aph);
+            aph ^= 1;
+            tc::tc_fence_after();
+            const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
+            for (int t = t0; t < t1; ++t) {
+                tc::mbar_wait(&tempty[as], tph ^ 1);
+                tc::mbar_wait(&full[stage], ph);
                 tc::tc_fence_after();
-                const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
-                for (int t = t0; t < t1; ++t) {
-                    tc::mbar_wait(&tempty[as], tph ^ 1);
-                    tc::mbar_wait(&full[stage], ph);
-                    tc::tc_fence_after();
-                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
-                    const uint64_t b0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
+                const uint32_t d_tmem = tmem_base + (uint32_t)(as * TILE_N);
+                const uint64_t b0 = tc::make_sw128_kmajor_desc(sB + stage * L::STAGE_BYTES);
+                if (tc::elect_one()) {
                     uint32_t accum = 0;
                     if (TERMS == 3) {                                      // cross terms first
+#pragma unroll 4
                         for (int ks = 0; ks < ksteps; ++ks) {
                             tc::mma_f16_ts(d_tmem, a_lo + ks * 8, b0 + boff(0, ks), idesc, accum); accum = 1;
                             tc::mma_f16_ts(d_tmem, a_hi + ks * 8, b0 + boff(1, ks), idesc, accum);
                         }
                     }
+#pragma unroll 4
                     for (int ks = 0; ks < ksteps; ++ks) {
                         tc::mma_f16_ts(d_tmem, a_hi + ks * 8, b0 + boff(0, ks), idesc, accum); accum = 1;
                     }
                     tc::mma_commit(&empty[stage]);
                     tc::mma_commit(&tfull[as]);
-                    if (++stage == STAGES) { stage = 0; ph ^= 1; }
-                    if (++as == ACC) { as = 0; tph ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == STAGES) { stage = 0; ph ^= 1; }
+                if (++as == ACC) { as = 0; tph ^= 1; }
             }
         }
     } else {
@@ -799,22 +814,25 @@ linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* 
                 tc::mbar_wait(&tfull[as], tph);
                 tc::tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(as * TILE_N + half * COLS);
-                float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+                // all of the warp's columns in flight at once, ONE wait, then the accumulator stage goes back to the MMA
+                // issuer before the arithmetic starts (the values are in registers)
+                float v[COLS];
 #pragma unroll
-                for (int c = 0; c < COLS; c += 32) {
-                    float v[32];
-                    tc::tmem_ld32(taddr + c, v);
-                    tc::tmem_ld_wait();
-#pragma unroll
-                    for (int j = 0; j < 32; j += 4) {
-                        s0 = fmaf(v[j], v[j], s0); s1 = fmaf(v[j + 1], v[j + 1], s1);
-                        s2 = fmaf(v[j + 2], v[j + 2], s2); s3 = fmaf(v[j + 3], v[j + 3], s3);
-                    }
-                }
+                for (int c = 0; c < COLS; c += 32) tc::tmem_ld32(taddr + c, *reinterpret_cast<float(*)[32]>(&v[c]));
+                tc::tmem_ld_wait();
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[as]);
-                accd += (double)((s0 + s1) + (s2 + s3));
+                float2 q[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+#pragma unroll
+                for (int j = 0; j < COLS; j += 8) {
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float2 t2 = make_float2(v[j + 2 * e], v[j + 2 * e + 1]);
+                        q[e] = ffma2(t2, t2, q[e]);
+                    }
+                }
+                accd += (double)(((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y)));
                 if (++as == ACC) { as = 0; tph ^= 1; }
             }
             // undo the chain's power-of-two scale (the accumulators hold (2^f x.d)^2 sums)
