@@ -732,6 +732,8 @@ def main():
                                      "ceiling_frac = algorithmic bytes / line-granular bytes of a perfect gather",
                         kernel_share_of_step=pinfo["step_kernel_ms"] / pinfo["device_ms"])
             acc_frac = pinfo["accepted"] / max(pinfo["proposals"], 1)
+        if roof is not None and world > 1:
+            roof["exchange"] = {k: v for k, v in s.kernel_info().items() if k in ("exchange", "memop_wait", "memop_write")}
         if roof is not None and pinfo.get("exchanges"):
             roof["exchange_us"] = 1e3 * pinfo["exchange_ms"] / pinfo["exchanges"]      # per K-block, this rank (device time of the push / all-gather)
 

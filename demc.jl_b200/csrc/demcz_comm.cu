@@ -16,6 +16,7 @@
 // high-priority side stream under the next K-block's step kernel.
 #include "demcz_internal.h"
 #include "demcz_sync.cuh"
+#include <cuda.h>
 #include <dlfcn.h>
 #include <unistd.h>
 #include <cstring>
@@ -65,6 +66,24 @@ NcclApi& api()
     SYM(GetErrorString, "ncclGetErrorString")
 #undef SYM
     return a;
+}
+
+// stream memory operations, resolved from the driver at run time (no link-time libcuda dependency)
+typedef CUresult (*StreamValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+struct MemOps { StreamValue32Fn wait = nullptr, write = nullptr; bool tried = false; };
+MemOps& memops()
+{
+    static MemOps m;
+    if (m.tried) return m;
+    m.tried = true;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        m.wait = reinterpret_cast<StreamValue32Fn>(p);
+    if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+        m.write = reinterpret_cast<StreamValue32Fn>(p);
+    cudaGetLastError();
+    return m;
 }
 
 int nccl_fail(demcz_ctx* c, const char* what, int rc)
@@ -117,8 +136,8 @@ extern "C" int demcz_comm_init(demcz_ctx* c, const uint8_t id[128])
             cudaEventCreateWithFlags(&c->ev_vis[i], cudaEventDisableTiming) != cudaSuccess)
             return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: cudaEventCreate");
     }
-    if (cudaMalloc((void**)&c->d_barrier, 4 * sizeof(unsigned long long)) != cudaSuccess ||
-        cudaMemset(c->d_barrier, 0, 4 * sizeof(unsigned long long)) != cudaSuccess)
+    if (cudaMalloc((void**)&c->d_barrier, 8 * sizeof(unsigned long long)) != cudaSuccess ||
+        cudaMemset(c->d_barrier, 0, 8 * sizeof(unsigned long long)) != cudaSuccess)
         return demcz_fail(c, DEMCZ_ERR_CUDA, "comm_init: barrier word");
     // NCCL connects lazily at the first collective of a communicator (hundreds of ms): pay for it here, not inside
     // the first Rhat / adaptγ reduction of a run
@@ -276,9 +295,30 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
         }
     }
     c->peers_open = true;
+    // stream memory operations (DEMCZ_MEMOPS=0 switches them off): probe the write on every peer's flag word of this rank
+    // (value 0 = its initial content) — a driver that refuses peer addresses leaves the one-warp publish kernel in place
+    {
+        const char* env = getenv("DEMCZ_MEMOPS");
+        const bool on = !(env && atoi(env) == 0);
+        MemOps& m = memops();
+        c->memop_wait = on && m.wait != nullptr;
+        c->memop_write = on && m.write != nullptr;
+        if (c->memop_write) {
+            for (int r = 0; r < c->o.world && c->memop_write; ++r) {
+                if (r == c->o.rank) continue;
+                unsigned long long* f = reinterpret_cast<unsigned long long*>(c->peerZ[r] + demcz_flag_off_floats(c)) + c->o.rank;
+                if (m.write((CUstream)c->comm_stream, (CUdeviceptr)(uintptr_t)f, 0u, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS) c->memop_write = false;
+            }
+            if (cudaStreamSynchronize(c->comm_stream) != cudaSuccess) { cudaGetLastError(); c->memop_write = false; }
+        }
+        if (c->memop_wait) {                     // and the wait on a local word that already holds the value
+            if (m.wait((CUstream)c->comm_stream, (CUdeviceptr)(uintptr_t)(c->d_barrier + 4), 0u, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS ||
+                cudaStreamSynchronize(c->comm_stream) != cudaSuccess) { cudaGetLastError(); c->memop_wait = false; }
+        }
+    }
     // every rank takes the same decision (same opts).  AUTO: the copy engines when a rank's rows are one contiguous
     // block of whole lines to every peer... measured choice, see DESIGN.md section 5
-    c->push_engine = c->o.push_engine == DEMCZ_PUSH_COPY_ENGINE ? 1 : 0;
+    c->push_engine = c->o.push_engine == DEMCZ_PUSH_KERNEL ? 0 : 1;             // AUTO: copy engines (measured)
     if (const char* env = getenv("DEMCZ_PUSH_ENGINE")) c->push_engine = (atoi(env) == DEMCZ_PUSH_COPY_ENGINE) ? 1 : 0;
     return DEMCZ_OK;
 }
@@ -311,7 +351,15 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
             for (int r = 0; r < np; ++r)
                 if (cudaMemcpyAsync(pp.p[r] + off, c->dZ + off, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
                     return demcz_fail(c, DEMCZ_ERR_CUDA, "peer copy of the appended rows failed: %s", cudaGetErrorString(cudaGetLastError()));
-            publish_flags_kernel<<<1, 32, 0, st>>>(pp, np, demcz_flag_off_floats(c), c->o.rank, seq);
+            if (c->memop_write) {                   // flag words by stream memory operations: ordered behind the copies, no SM needed
+                for (int r = 0; r < np; ++r) {
+                    unsigned long long* f = reinterpret_cast<unsigned long long*>(pp.p[r] + demcz_flag_off_floats(c)) + c->o.rank;
+                    if (memops().write((CUstream)st, (CUdeviceptr)(uintptr_t)f, (cuuint32_t)seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                        return demcz_fail(c, DEMCZ_ERR_CUDA, "cuStreamWriteValue32 on a peer flag word failed");
+                }
+            } else {
+                publish_flags_kernel<<<1, 32, 0, st>>>(pp, np, demcz_flag_off_floats(c), c->o.rank, seq);
+            }
         } else {
             const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
             const long long total = (long long)c->o.N * C;
@@ -356,6 +404,13 @@ int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n)
     if (c->o.world == 1) return DEMCZ_OK;
     int rc = api().AllReduce(dev, dev, (size_t)n, ncclUint64, ncclSum, (ncclComm_t)c->comm, c->stream);
     if (rc != ncclSuccess) return nccl_fail(c, "ncclAllReduce", rc);
+    return DEMCZ_OK;
+}
+
+int demcz_comm_wait_done_word(demcz_ctx* c, unsigned int seq)
+{
+    if (memops().wait((CUstream)c->comm_stream, (CUdeviceptr)(uintptr_t)(c->d_barrier + 4), (cuuint32_t)seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+        return demcz_fail(c, DEMCZ_ERR_CUDA, "cuStreamWaitValue32 failed");
     return DEMCZ_OK;
 }
 

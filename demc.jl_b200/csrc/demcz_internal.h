@@ -92,6 +92,11 @@ struct demcz_ctx {
     bool peers_open = false;
     int64_t appends = 0;                         // archive appends so far (overlap mode: visibility lags by one)
     int64_t vis_waited = 0;
+    // stream memory operations (cuStreamWaitValue32 / cuStreamWriteValue32): the side stream waits on a word the appending
+    // step kernel writes (no event on the compute stream -> consecutive step kernels keep their programmatic overlap) and
+    // publishes the segment flags without a kernel (no SM slot needed while the step kernel fills the GPU)
+    bool memop_wait = false, memop_write = false;
+    bool last_append_by_step_kernel = false;     // the segment just appended carries a done word (closed-form path)
     int push_engine = 0;                         // 0: our push kernel (SM stores over NVLink), 1: copy engines (one peer copy per rank) + flag kernel
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)
     bool persistent_ok = false;                  // small-N persistent launches in effect (opts.persistent)
@@ -127,6 +132,7 @@ int demcz_hist_end(demcz_ctx* c, int64_t g, int n_gens);
 
 // demcz_comm.cu — no-ops when world == 1
 int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side);
+int demcz_comm_wait_done_word(demcz_ctx* c, unsigned int seq);   // side stream: cuStreamWaitValue32 on the step kernel's done word
 int demcz_comm_wait_segment(demcz_ctx* c, int64_t nseg);     // stream-ordered wait (end of a run; the step kernels poll the flags themselves)
 // how many segments must have landed from every peer before the next gathering launch (0: no wait); see demcz_archive_view
 unsigned long long demcz_comm_need(const demcz_ctx* c);

@@ -646,8 +646,13 @@ int demcz_archive_appended(demcz_ctx* c)
     if (o.world > 1) {
         if (o.sync_mode == DEMCZ_SYNC_OVERLAP) {
             const int slot = (int)(c->appends & 1);
-            CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
-            CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
+            if (c->last_append_by_step_kernel) {         // the side stream waits on the word the kernel's last CTA writes
+                int rc = demcz_comm_wait_done_word(c, (unsigned int)(c->appends + 1));
+                if (rc != DEMCZ_OK) return rc;
+            } else {
+                CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
+                CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
+            }
             int rc = demcz_comm_exchange(c, row0, true);
             if (rc != DEMCZ_OK) return rc;
             CU(c, cudaEventRecord(c->ev_vis[slot], c->comm_stream));
@@ -871,6 +876,13 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.thin = c->thin; a.hist_phase = (int)(g % c->thin); a.hist_idx0 = (unsigned int)(g / c->thin);
             a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank;
             a.need = demcz_comm_need(c);
+            c->last_append_by_step_kernel = false;
+            if (append && o.world > 1 && c->memop_wait && o.sync_mode == DEMCZ_SYNC_OVERLAP) {
+                a.done_word = (unsigned int*)(c->d_barrier + 4);
+                a.done_ctr = (unsigned int*)(c->d_barrier + 5);
+                a.done_seq = (unsigned int)(c->appends + 1);
+                c->last_append_by_step_kernel = true;
+            }
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             CU(c, demcz_launch_step(c, a, acc, full));
             if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
@@ -962,6 +974,11 @@ extern "C" int demcz_get_kernel_info(demcz_ctx* c, char* buf, int64_t len)
     if (!c) return DEMCZ_ERR_INVALID;
     std::string s = demcz_linreg_info(c);
     s += c->persistent_ok ? "step_persistent=1;" : "step_persistent=0;";
+    if (c->o.world > 1) {
+        s += !c->peers_open ? "exchange=nccl_allgather;" : c->push_engine == 1 ? "exchange=copy_engine;" : "exchange=push_kernel;";
+        s += c->memop_wait ? "memop_wait=1;" : "memop_wait=0;";
+        s += c->memop_write ? "memop_write=1;" : "memop_write=0;";
+    }
     if (buf && len > 0) {
         const size_t n = std::min<size_t>(s.size(), (size_t)len - 1);
         memcpy(buf, s.data(), n);

@@ -83,6 +83,12 @@ struct StepArgs {
     const unsigned long long* flags;
     int world, my_rank;
     unsigned long long need;
+    // appending launches of a sharded run: the last CTA to finish publishes `done_seq` in `done_word` (release, gpu
+    // scope) — the side stream waits on that word (stream memory operation) before it moves the rows to the peers,
+    // so the compute stream carries nothing but step kernels.  done_word == nullptr: not used.
+    unsigned int* done_word;
+    unsigned int* done_ctr;
+    unsigned int done_seq;
 };
 
 // Packed-FP32 (f32x2) arithmetic: one issue slot per two FMAs (SASS FFMA2 / FADD2 / FMUL2 on sm_100a).
@@ -489,6 +495,16 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     }
     if (ACC && threadIdx.x < a.d) atomicAdd(&a.S2[threadIdx.x], (double)red_s2[threadIdx.x]);
 
+    if (a.done_word) {                           // the __syncthreads above ordered every thread's append stores before this point
+        if (threadIdx.x == 0) {
+            __threadfence();                     // cumulative: the CTA's rows are visible at gpu scope before the ticket
+            if (atomicAdd(a.done_ctr, 1u) == gridDim.x - 1) {
+                *a.done_ctr = 0u;
+                __threadfence();                 // acquire side of the ticket: every CTA's rows happen-before the word
+                asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(a.done_word), "r"(a.done_seq) : "memory");
+            }
+        }
+    }
 }
 
 // Batched log-density: map(logobj, rows) (src/demcz.jl:17).  X SoA [k][ldx].
