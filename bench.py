@@ -423,7 +423,7 @@ def main():
         return w, gps, _cfg(w, gps)
 
     # what DEMCZ_XCHG_AUTO resolves to (include/demcz.h): rows without slot padding above 4 GPUs
-    eff_layout = args.exchange_layout if args.exchange_layout != "auto" else ("dense_slots" if world > 4 else "in_place")
+    eff_layout = args.exchange_layout if args.exchange_layout != "auto" else ("dense_slots" if world >= 4 else "in_place")
 
     def _cfg(w, gps):
         K = w["K"]

@@ -160,6 +160,7 @@ void demcz_comm_destroy_internal(demcz_ctx* c)
         if (c->ev_app[i]) cudaEventDestroy(c->ev_app[i]);
         if (c->ev_vis[i]) cudaEventDestroy(c->ev_vis[i]);
     }
+    for (int i = 1; i < 8; ++i) if (c->xs[i]) cudaStreamDestroy(c->xs[i]);
     if (c->comm_stream) cudaStreamDestroy(c->comm_stream);
     if (c->d_barrier) cudaFree(c->d_barrier);
 }
@@ -316,10 +317,25 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
                 cudaStreamSynchronize(c->comm_stream) != cudaSuccess) { cudaGetLastError(); c->memop_wait = false; }
         }
     }
-    // every rank takes the same decision (same opts).  AUTO: the copy engines when a rank's rows are one contiguous
-    // block of whole lines to every peer... measured choice, see DESIGN.md section 5
-    c->push_engine = c->o.push_engine == DEMCZ_PUSH_KERNEL ? 0 : 1;             // AUTO: copy engines (measured)
+    // every rank takes the same decision (same opts, same driver).  AUTO: copy engines (measured)
+    c->push_engine = c->o.push_engine == DEMCZ_PUSH_KERNEL ? 0 : 1;
     if (const char* env = getenv("DEMCZ_PUSH_ENGINE")) c->push_engine = (atoi(env) == DEMCZ_PUSH_COPY_ENGINE) ? 1 : 0;
+    c->inkernel_poll = c->push_engine == 1 && c->memop_write;
+    if (!c->inkernel_poll) c->memop_wait = false;                  // the wait kernel path keeps the event hand-off
+    c->xs[0] = c->comm_stream;
+    c->n_xs = 1;
+    if (c->push_engine == 1) {
+        // one copy engine moves ~300-350 GB/s next to the step kernel (measured); one stream per peer lets several
+        // engines work at once (3 streams on 4 GPUs: 580 GB/s aggregate)
+        int want = std::min(7, c->o.world - 1);
+        if (const char* env = getenv("DEMCZ_CE_STREAMS")) want = std::max(1, std::min(7, atoi(env)));
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);
+        for (int i = 1; i < want; ++i) {
+            if (cudaStreamCreateWithPriority(&c->xs[i], cudaStreamNonBlocking, hi) != cudaSuccess) { cudaGetLastError(); break; }
+            c->n_xs = i + 1;
+        }
+    }
     return DEMCZ_OK;
 }
 
@@ -345,20 +361,24 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
         for (int r = 0; r < c->o.world; ++r) if (r != c->o.rank) pp.p[np++] = c->peerZ[r];
         mark();
         if (c->push_engine == 1) {
-            // one contiguous copy per peer: this rank's N row slots (with dense slots: payload only)
+            // one contiguous copy per peer: this rank's N row slots (with dense slots: payload only).  Peers in ROTATED
+            // order (rank+1, rank+2, ...): at any moment every destination is written by one sender, not by all of them
+            // (incast on one ingress link); on the side stream(s) round-robin, the peer's flag word right behind its copy
             const size_t off = (size_t)(phys_row0 + c->o.chain_offset) * c->ZS;
             const size_t bytes = (size_t)c->o.N * c->ZS * sizeof(float);
-            for (int r = 0; r < np; ++r)
-                if (cudaMemcpyAsync(pp.p[r] + off, c->dZ + off, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess)
+            for (int i = 1; i < c->o.world; ++i) {
+                const int r = (c->o.rank + i) % c->o.world;
+                cudaStream_t xs = side ? c->xs[(i - 1) % c->n_xs] : st;
+                if (cudaMemcpyAsync(c->peerZ[r] + off, c->dZ + off, bytes, cudaMemcpyDeviceToDevice, xs) != cudaSuccess)
                     return demcz_fail(c, DEMCZ_ERR_CUDA, "peer copy of the appended rows failed: %s", cudaGetErrorString(cudaGetLastError()));
-            if (c->memop_write) {                   // flag words by stream memory operations: ordered behind the copies, no SM needed
-                for (int r = 0; r < np; ++r) {
-                    unsigned long long* f = reinterpret_cast<unsigned long long*>(pp.p[r] + demcz_flag_off_floats(c)) + c->o.rank;
-                    if (memops().write((CUstream)st, (CUdeviceptr)(uintptr_t)f, (cuuint32_t)seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
+                if (c->memop_write) {               // flag word by a stream memory operation: ordered behind the copy, no SM needed
+                    unsigned long long* f = reinterpret_cast<unsigned long long*>(c->peerZ[r] + demcz_flag_off_floats(c)) + c->o.rank;
+                    if (memops().write((CUstream)xs, (CUdeviceptr)(uintptr_t)f, (cuuint32_t)seq, CU_STREAM_WRITE_VALUE_DEFAULT) != CUDA_SUCCESS)
                         return demcz_fail(c, DEMCZ_ERR_CUDA, "cuStreamWriteValue32 on a peer flag word failed");
+                } else {
+                    PeerPtrs one; one.p[0] = c->peerZ[r];
+                    publish_flags_kernel<<<1, 32, 0, xs>>>(one, 1, demcz_flag_off_floats(c), c->o.rank, seq);
                 }
-            } else {
-                publish_flags_kernel<<<1, 32, 0, st>>>(pp, np, demcz_flag_off_floats(c), c->o.rank, seq);
             }
         } else {
             const int C = c->LD / 4;       // payload pieces only (rounding up to whole 32-byte sectors costs bytes and gains nothing: measured)
@@ -386,7 +406,7 @@ int demcz_comm_exchange(demcz_ctx* c, int64_t phys_row0, bool side)
 // Only the peer-push transport uses flag words; the NCCL all-gather is ordered by its stream / events.
 unsigned long long demcz_comm_need(const demcz_ctx* c)
 {
-    if (c->o.world == 1 || !c->peers_open) return 0ull;
+    if (c->o.world == 1 || !c->peers_open || !c->inkernel_poll) return 0ull;
     const int64_t n = c->o.sync_mode == DEMCZ_SYNC_OVERLAP ? c->appends - 1 : c->appends;
     return n > 0 ? (unsigned long long)n : 0ull;
 }
@@ -409,8 +429,9 @@ int demcz_comm_allreduce_u64(demcz_ctx* c, unsigned long long* dev, int n)
 
 int demcz_comm_wait_done_word(demcz_ctx* c, unsigned int seq)
 {
-    if (memops().wait((CUstream)c->comm_stream, (CUdeviceptr)(uintptr_t)(c->d_barrier + 4), (cuuint32_t)seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
-        return demcz_fail(c, DEMCZ_ERR_CUDA, "cuStreamWaitValue32 failed");
+    for (int i = 0; i < c->n_xs; ++i)
+        if (memops().wait((CUstream)c->xs[i], (CUdeviceptr)(uintptr_t)(c->d_barrier + 4), (cuuint32_t)seq, CU_STREAM_WAIT_VALUE_GEQ) != CUDA_SUCCESS)
+            return demcz_fail(c, DEMCZ_ERR_CUDA, "cuStreamWaitValue32 failed");
     return DEMCZ_OK;
 }
 

@@ -96,6 +96,13 @@ struct demcz_ctx {
     // step kernel writes (no event on the compute stream -> consecutive step kernels keep their programmatic overlap) and
     // publishes the segment flags without a kernel (no SM slot needed while the step kernel fills the GPU)
     bool memop_wait = false, memop_write = false;
+    // The gathering kernels may spin on the peers' flag words ONLY if publishing a segment needs no SM on the sending GPU
+    // (copy engines + cuStreamWriteValue32): a publish/push KERNEL could find every SM slot of its GPU held by that GPU's
+    // own spinning step kernel -> all ranks wait for each other (observed: 8 GPUs, timed out in flag_wait).  Otherwise a
+    // one-warp wait kernel sits between the step kernels (it holds one slot only).
+    bool inkernel_poll = false;
+    cudaStream_t xs[8] = {nullptr};                 // copy-engine transport: side streams (xs[0] = comm_stream), up to one per peer
+    int n_xs = 1;
     bool last_append_by_step_kernel = false;     // the segment just appended carries a done word (closed-form path)
     int push_engine = 0;                         // 0: our push kernel (SM stores over NVLink), 1: copy engines (one peer copy per rank) + flag kernel
     int64_t appends_run = 0;                     // appends since create (set_archive does not reset it)

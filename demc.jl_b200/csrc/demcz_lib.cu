@@ -370,7 +370,7 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
     c->LD = (o->d + 3) / 4 * 4;
     c->ZS = o->d <= DEMCZ_MAX_DIM ? zslot(c->LD) : c->LD;
     // rows back to back instead of padded slots when the exchange rather than the gather bounds a K-block (demcz.h)
-    if (o->exchange_layout == DEMCZ_XCHG_DENSE_SLOTS || (o->exchange_layout == DEMCZ_XCHG_AUTO && o->world > 4)) c->ZS = c->LD;
+    if (o->exchange_layout == DEMCZ_XCHG_DENSE_SLOTS || (o->exchange_layout == DEMCZ_XCHG_AUTO && o->world >= 4)) c->ZS = c->LD;
     c->ldx = (o->N + 31) / 32 * 32;
     c->keys = make_philox_keys(o->seed);
     if (const char* gr = getenv("DEMCZ_L2_FETCH")) cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(gr));
@@ -635,6 +635,15 @@ int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart)
         CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 2) & 1], 0));
         c->vis_waited = c->appends - 1;
     }
+    if (o.world > 1 && c->peers_open && !c->inkernel_poll) {
+        // peer transport without in-kernel polling: a one-warp wait kernel in front of the gathering launch
+        const int64_t need = overlap ? c->appends - 1 : c->appends;
+        if (need > c->vis_waited) {
+            int rc = demcz_comm_wait_segment(c, need);
+            if (rc != DEMCZ_OK) return rc;
+            c->vis_waited = need;
+        }
+    }
     return DEMCZ_OK;
 }
 
@@ -651,7 +660,8 @@ int demcz_archive_appended(demcz_ctx* c)
                 if (rc != DEMCZ_OK) return rc;
             } else {
                 CU(c, cudaEventRecord(c->ev_app[slot], c->stream));
-                CU(c, cudaStreamWaitEvent(c->comm_stream, c->ev_app[slot], 0));
+                for (int i = 0; i < std::max(1, c->n_xs); ++i)
+                    CU(c, cudaStreamWaitEvent(c->xs[i] ? c->xs[i] : c->comm_stream, c->ev_app[slot], 0));
             }
             int rc = demcz_comm_exchange(c, row0, true);
             if (rc != DEMCZ_OK) return rc;
@@ -921,6 +931,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         }
     }
     if (o.world > 1) {                                                       // drain the exchange: the archive is complete when the call returns
+        for (int i = 0; i < 8; ++i) if (c->xs[i]) CU(c, cudaStreamSynchronize(c->xs[i]));      // this rank's own transfers
         if (o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends > 0) CU(c, cudaStreamWaitEvent(c->stream, c->ev_vis[(c->appends - 1) & 1], 0));
         rc = demcz_comm_wait_segment(c, c->appends);
         if (rc != DEMCZ_OK) return rc;
