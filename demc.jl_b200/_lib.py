@@ -48,7 +48,7 @@ class RunInfo(C.Structure):
 
 EXPORTS = [
     "demcz_version", "demcz_create", "demcz_destroy", "demcz_last_error", "demcz_set_likelihood_mvnormal",
-    "demcz_set_likelihood_linreg", "demcz_set_archive", "demcz_set_state", "demcz_set_temperature_table",
+    "demcz_set_likelihood_linreg", "demcz_set_likelihood_logistic", "demcz_set_archive", "demcz_set_state", "demcz_set_temperature_table",
     "demcz_run", "demcz_get_kernel_info", "demcz_set_profile", "demcz_get_chain", "demcz_get_state", "demcz_get_archive", "demcz_get_moments", "demcz_get_archive_moments",
     "demcz_get_history_moments", "demcz_get_archive_checksum", "demcz_get_rhat",
     "demcz_get_accept_counts", "demcz_eval_logdensity", "demcz_get_trace", "demcz_comm_unique_id", "demcz_comm_init", "demcz_comm_peer_info", "demcz_comm_open_peers",
@@ -75,6 +75,7 @@ def load():
     lib.demcz_destroy.restype = None
     lib.demcz_set_likelihood_mvnormal.argtypes = [vp, C.c_int32, dp, dp, C.c_int32]
     lib.demcz_set_likelihood_linreg.argtypes = [vp, i64, C.c_int32, dp, dp]
+    lib.demcz_set_likelihood_logistic.argtypes = [vp, i64, C.c_int32, dp, dp]
     lib.demcz_set_archive.argtypes = [vp, dp, i64]
     lib.demcz_set_state.argtypes = [vp, dp, dp]
     lib.demcz_set_temperature_table.argtypes = [vp, dp, i64]

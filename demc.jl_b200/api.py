@@ -26,7 +26,7 @@ import numpy as np
 
 from . import _lib
 
-__all__ = ["DEMCopt", "demcopt", "MC", "MvNormalLogpdf", "QuadraticLogobj", "LinRegLoglik", "demcz_sample",
+__all__ = ["DEMCopt", "demcopt", "MC", "MvNormalLogpdf", "QuadraticLogobj", "LinRegLoglik", "LogisticLoglik", "demcz_sample",
            "demcz_anneal", "demcz_sample_par", "demcz_anneal_par", "tempbaseline", "Sampler"]
 
 
@@ -120,6 +120,14 @@ class LinRegLoglik:
         return lib.demcz_set_likelihood_linreg(ctx, self.n, self.d, _dp(self.X), _dp(self.y))
 
 
+class LogisticLoglik(LinRegLoglik):
+    """sum(y .* eta .- log1p.(exp.(eta))), eta = X*b — Bernoulli-logit GLM on the same tensor-core contraction as
+    LinRegLoglik with a softplus epilogue (an extension: the reference takes any closure, src/demcz.jl:189)."""
+
+    def _register(self, lib, ctx):
+        return lib.demcz_set_likelihood_logistic(ctx, self.n, self.d, _dp(self.X), _dp(self.y))
+
+
 def tempbaseline(ig, Ng, T0, TN):
     """src/demcz_anneal.jl:1-3"""
     return T0 * (TN / T0) ** (ig / Ng)
@@ -132,7 +140,7 @@ def _dp(a):
 def _check_likelihood(logobj):
     if not hasattr(logobj, "_register"):
         raise TypeError(
-            "logobj must be a registered GPU likelihood descriptor (MvNormalLogpdf, QuadraticLogobj, LinRegLoglik); "
+            "logobj must be a registered GPU likelihood descriptor (MvNormalLogpdf, QuadraticLogobj, LinRegLoglik, LogisticLoglik); "
             "arbitrary closures are not supported and there is no CPU fallback")
 
 

@@ -155,7 +155,8 @@ int demcz_moments_get(demcz_ctx* c, double* mean, double* cov, int64_t* n, int32
 // demcz_linreg.cu
 // out_dev == nullptr: evaluate the context's own N chains into its FP64 log-objective array
 int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_dev);
-int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half);
+int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half, bool snooker = false);
+bool demcz_is_snooker_gen(const demcz_ctx* c, long long gen_abs);
 void demcz_linreg_free(demcz_ctx* c);
 double* demcz_linreg_lp(demcz_ctx* c);           // [ldx] FP64 log-objective of the chains (logpi ~ -n/2 needs more than FP32)
 double* demcz_linreg_lphist(demcz_ctx* c);       // [G][N]

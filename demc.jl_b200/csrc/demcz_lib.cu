@@ -305,7 +305,164 @@ cudaError_t launch_eval(demcz_ctx* c, const float* X, int n, int ldx, float* out
 
 inline int grid1d(long long n, int threads = 256) { return (int)((n + threads - 1) / threads); }
 
+// ------------------------------------------------------------------------------------------------
+// Snooker generation (ter Braak & Vrugt 2008, the update the reference's README cites but does not implement:
+// README.md:57-59): one proposal per chain along the line through the chain and an archive point z,
+//     x' = x + gamma_s * e * ((z1 - z2) . e) / (e . e),   e = x - z,   z, z1, z2 three distinct archive rows,
+// accepted with probability min(1, pi(x')/pi(x) * (|x' - z| / |x - z|)^(d-1)); |x' - z| / |x - z| = |1 + gamma_s proj|.
+// Ignores the block structure (moves all coordinates).  A generation is a snooker generation as a whole (chosen from
+// the Philox stream by the host), so the fused step kernel is untouched; this kernel is thread-per-chain.
+// ------------------------------------------------------------------------------------------------
+struct SnookerArgs {
+    float* X; float* logp; int N, ldx, d;
+    uint32_t chain_offset;
+    const float* Z; int ZS; uint32_t Mdraw, zstart, zcap;
+    long long gen, grel;
+    PhiloxKeys keys;
+    float gamma_s;                 // 0: uniform on [1.2, 2.2]
+    const float* Ttab;             // temperature table or nullptr
+    int nblocks;                   // trace layout only
+    float* hist; float* lphist; long long hidx;      // history slot of this generation or hist == nullptr
+    uint32_t *tr_r1, *tr_r2; float *tr_u, *tr_xprop, *tr_lpprop; uint8_t* tr_acc;
+    int* chain_changed; unsigned long long *win_changed, *accepted_total; int count_run, count_win;
+    float* S1; double* S2; float shift[32];
+    float* Zw; uint32_t append_row0;
+    const unsigned long long* flags; int world, my_rank; unsigned long long need;
+};
+
+template <int LD>
+__global__ void snooker_mvn_kernel(const __grid_constant__ SnookerArgs a, const __grid_constant__ MvnParams<LD> P)
+{
+    __shared__ unsigned int red[2];
+    __shared__ float red_s2[LD];
+    wait_peer_segments(a.flags, a.world, a.my_rank, a.need);
+    if (threadIdx.x < 2) red[threadIdx.x] = 0u;
+    if (threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = chain < a.N;
+    const int cl = active ? chain : a.N - 1;
+    const uint32_t cid = a.chain_offset + (uint32_t)cl;
+    const uint32_t g_lo = (uint32_t)a.gen, g_hi = (uint32_t)((unsigned long long)a.gen >> 32);
+    float x[LD];
+#pragma unroll
+    for (int k = 0; k < LD; ++k) x[k] = k < a.d ? a.X[(size_t)k * a.ldx + cl] : 0.f;
+    const float lp = a.logp[cl];
+
+    const u32x4 w = philox4x32_10(cid, g_lo, kSnookerCall, g_hi, a.keys);
+    uint32_t z, z1, z2;
+    draw_triple(__umulhi(w.x, a.Mdraw), __umulhi(w.y, a.Mdraw - 1u), __umulhi(w.z, a.Mdraw - 2u), z, z1, z2);
+    float gs = a.gamma_s;
+    if (gs == 0.f) gs = 1.2f + uniform01(philox4x32_10(cid, g_lo, kSnookerCall + 1u, g_hi, a.keys).x);
+    auto phys = [&](uint32_t r) { r += a.zstart; if (r >= a.zcap) r -= a.zcap; return a.Z + (size_t)r * a.ZS; };
+    const float *pz = phys(z), *p1 = phys(z1), *p2 = phys(z2);
+    float ee = 0.f, num = 0.f, e[LD];
+#pragma unroll
+    for (int k = 0; k < LD; ++k) {
+        const float zk = k < a.d ? pz[k] : 0.f, dk = k < a.d ? p1[k] - p2[k] : 0.f;
+        e[k] = x[k] - zk;
+        ee = fmaf(e[k], e[k], ee);
+        num = fmaf(dk, e[k], num);
+    }
+    const float proj = ee > 0.f ? gs * (num / ee) : 0.f;              // x == z: no direction, the proposal is x itself (rejected below)
+    float2 xp2[LD / 2];
+#pragma unroll
+    for (int k = 0; k < LD; k += 2) xp2[k / 2] = make_float2(fmaf(proj, e[k], x[k]), fmaf(proj, e[k + 1], x[k + 1]));
+    const float lpp = mvn_logdensity<LD, false>(P.W, P.mu2, P.c0, xp2);
+    const float geo = (float)(a.d - 1) * __logf(fabsf(1.f + proj));   // (d-1) log(|x'-z| / |x-z|); -inf when x' = z
+    const float u = uniform01(w.w);
+    const float logu = __logf(u);
+    const float T = a.Ttab ? a.Ttab[a.grel - 1] : 1.f;
+    const bool acc = ee > 0.f && (logu * T < (lpp - lp) + T * geo);   // NaN -> reject; T = 0 -> greedy on the objective
+
+    if (a.tr_r1 && active) {
+        const size_t o = ((size_t)(a.grel - 1) * a.nblocks) * a.N + chain;      // block slot 0 of this generation
+        a.tr_r1[o] = z1; a.tr_r2[o] = z2; a.tr_u[o] = u; a.tr_lpprop[o] = lpp; a.tr_acc[o] = acc ? 1 : 0;
+#pragma unroll
+        for (int k = 0; k < LD; ++k)
+            if (k < a.d) a.tr_xprop[(((size_t)(a.grel - 1) * a.nblocks) * a.d + k) * a.N + chain] = (k & 1) ? xp2[k / 2].y : xp2[k / 2].x;
+    }
+    float lpn = lp;
+    if (acc) {
+#pragma unroll
+        for (int k = 0; k < LD; ++k) x[k] = (k & 1) ? xp2[k / 2].y : xp2[k / 2].x;
+        lpn = lpp;
+    }
+    if (active) {
+        if (acc) {
+#pragma unroll
+            for (int k = 0; k < LD; ++k) if (k < a.d) a.X[(size_t)k * a.ldx + chain] = x[k];
+            a.logp[chain] = lpn;
+        }
+        if (acc && lpn != lp && a.count_run) a.chain_changed[chain] += 1;      // generations whose log-objective changed (src/utils.jl:61)
+        if (a.hist) {
+#pragma unroll
+            for (int k = 0; k < LD; ++k) if (k < a.d) a.hist[((size_t)a.hidx * a.d + k) * a.N + chain] = x[k];
+            a.lphist[(size_t)a.hidx * a.N + chain] = lpn;
+        }
+        if (a.Zw) {
+            uint32_t row = a.append_row0 + a.chain_offset + (uint32_t)chain;
+            if (row >= a.zcap) row -= a.zcap;
+            float* dst = a.Zw + (size_t)row * a.ZS;
+#pragma unroll
+            for (int k = 0; k < LD; ++k) dst[k] = x[k];             // LD <= ZS: the 16-byte padded row
+        }
+    }
+    const bool changed = active && acc && lpn != lp;
+    if (a.S1) {
+#pragma unroll
+        for (int k = 0; k < LD; ++k) {
+            if (k < a.d) {                                         // warp-uniform
+                const float t = active ? x[k] - a.shift[k] : 0.f;
+                if (active) a.S1[(size_t)k * a.ldx + chain] += t;
+                const float v = warp_sum(t * t);
+                if ((threadIdx.x & 31) == 0) atomicAdd(&red_s2[k], v);
+            }
+        }
+    }
+    const int wa = warp_sum((acc && active) ? 1 : 0), ww = warp_sum((changed && a.count_win) ? 1 : 0);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&red[0], (unsigned)wa); atomicAdd(&red[1], (unsigned)ww); }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (red[0]) atomicAdd(a.accepted_total, (unsigned long long)red[0]);
+        if (red[1]) atomicAdd(a.win_changed, (unsigned long long)red[1]);
+    }
+    if (a.S1 && threadIdx.x < a.d) atomicAdd(&a.S2[threadIdx.x], (double)red_s2[threadIdx.x]);
+}
+
+template <int LD>
+cudaError_t launch_snooker_t(demcz_ctx* c, const SnookerArgs& a)
+{
+    const MvnParams<LD> P = demcz_make_mvn_params<LD>(c, false);
+    snooker_mvn_kernel<LD><<<(a.N + 127) / 128, 128, 0, c->stream>>>(a, P);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_snooker(demcz_ctx* c, const SnookerArgs& a)
+{
+    switch (c->LD) {
+        case 4:  return launch_snooker_t<4>(c, a);
+        case 8:  return launch_snooker_t<8>(c, a);
+        case 12: return launch_snooker_t<12>(c, a);
+        case 16: return launch_snooker_t<16>(c, a);
+        case 20: return launch_snooker_t<20>(c, a);
+        case 24: return launch_snooker_t<24>(c, a);
+        case 28: return launch_snooker_t<28>(c, a);
+        case 32: return launch_snooker_t<32>(c, a);
+    }
+    return cudaErrorInvalidValue;
+}
+
 }  // namespace
+
+// Is generation `gen_abs` (absolute, 1-based) a snooker generation?  Same answer on every rank and in the oracle.
+bool demcz_is_snooker_gen(const demcz_ctx* c, long long gen_abs)
+{
+    if (!(c->o.snooker_prob > 0.0)) return false;
+    const u32x4 w = philox4x32_10_host(0xFFFFFFFFu, (uint32_t)gen_abs, kSnookerCall, (uint32_t)((unsigned long long)gen_abs >> 32), c->keys);
+    const double u = ((double)(w.x >> 9) + 0.5) * (1.0 / 8388608.0);
+    return u < c->o.snooker_prob;
+}
 
 // ------------------------------------------------------------------------------------------------
 // ABI: lifecycle
@@ -816,7 +973,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     int64_t g_end = o.Ngeneration;
     if (max_generations > 0 && g_begin + max_generations < g_end) g_end = g_begin + max_generations;
     const int every = o.autostop_every, nhalf = every / 2;
-    size_t n_launch = 0;
+    size_t n_launch = 0, n_launch_untimed = 0;     // step-kernel launches (bracketed by events under profile=1) / snooker launches
     c->xchg_used = 0;
     const unsigned long long lin_launch0 = demcz_linreg_launches(c);
     if (c->lik_kind == DEMCZ_LIK_LINREG) demcz_linreg_profile_ms(c, nullptr);      // drop brackets of earlier calls
@@ -840,12 +997,49 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         // opts.moments on the closed-form path: one generation per launch, the state is added to the accumulators
         // after every launch (exact mean_cov_chain of the full history; the linreg path already runs per generation)
         if (o.moments && c->lik_kind != DEMCZ_LIK_LINREG) gb = g + 1;
+        // snooker generations (opts.snooker_prob) run in their own launch: stop the fused launch in front of the next one
+        bool snk = false;
+        if (o.snooker_prob > 0.0) {
+            if (demcz_is_snooker_gen(c, o.gen_offset + g + 1)) { snk = true; gb = g + 1; }
+            else for (int64_t t = g + 1; t < gb; ++t) if (demcz_is_snooker_gen(c, o.gen_offset + t + 1)) { gb = t; break; }
+        }
         const int n_gens = (int)(gb - g);
         const bool append = (gb % o.K) == 0;
 
         if (c->lik_kind == DEMCZ_LIK_LINREG) {
-            rc = demcz_linreg_generations(c, g, n_gens, append, acc, half);
+            rc = demcz_linreg_generations(c, g, n_gens, append, acc, half, snk);
             if (rc != DEMCZ_OK) return rc;
+        } else if (snk) {
+            SnookerArgs a;
+            memset(&a, 0, sizeof a);
+            a.X = c->dX; a.logp = c->dlogp; a.N = o.N; a.ldx = c->ldx; a.d = o.d;
+            a.chain_offset = (uint32_t)o.chain_offset;
+            a.Z = c->dZ; a.ZS = c->ZS; a.zcap = (uint32_t)c->zcap;
+            rc = demcz_archive_view(c, &a.Mdraw, &a.zstart);
+            if (rc != DEMCZ_OK) return rc;
+            if (a.Mdraw < 3) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: the snooker update needs 3 drawable archive rows");
+            a.gen = o.gen_offset + g + 1; a.grel = g + 1;
+            a.keys = c->keys;
+            a.gamma_s = (float)o.snooker_gamma;
+            a.Ttab = o.anneal ? c->dT : nullptr;
+            a.nblocks = o.Nblocks;
+            { void* lph = nullptr; float* h = nullptr; rc = demcz_hist_begin(c, g, 1, &h, &lph); if (rc != DEMCZ_OK) return rc;
+              const bool keep = h != nullptr && (g + 1) % c->thin == 0;
+              a.hist = keep ? h : nullptr; a.lphist = (float*)lph; a.hidx = (g + 1) / c->thin - 1; }
+            a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop; a.tr_lpprop = c->tr_lpprop; a.tr_acc = c->tr_acc;
+            a.chain_changed = c->d_chain_changed; a.win_changed = c->d_counters + 0; a.accepted_total = c->d_counters + 1;
+            a.count_run = (g == 0) ? 0 : 1;
+            a.count_win = (o.anneal && o.adapt && g % o.adapt_every == 0) ? 0 : 1;
+            if (acc) { a.S1 = c->dS1[half]; a.S2 = c->dS2 + (size_t)half * o.d; for (int k = 0; k < 32; ++k) a.shift[k] = c->shift[k]; }
+            a.Zw = append ? c->dZ : nullptr;
+            a.append_row0 = (uint32_t)(c->M % c->zcap);
+            a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank; a.need = demcz_comm_need(c);
+            c->last_append_by_step_kernel = false;
+            CU(c, launch_snooker(c, a));
+            ++n_launch_untimed;
+            rc = demcz_hist_end(c, g, 1);
+            if (rc != DEMCZ_OK) return rc;
+            if (o.moments) { rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
         } else {
             // ---- launch ------------------------------------------------------------------------
             StepArgs a;
@@ -901,7 +1095,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (rc != DEMCZ_OK) return rc;
             if (o.moments) { rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
         }
-        c->proposals += (int64_t)n_gens * o.Nblocks * o.N;
+        c->proposals += snk ? (int64_t)o.N : (int64_t)n_gens * o.Nblocks * o.N;        // a snooker generation is one proposal per chain
 
         // ---- archive append + exchange (src/demcz.jl:88-91; sync mode :129-137) -----------------
         if (append) {
@@ -955,7 +1149,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
         unsigned long long acc_total = 0;
         CU(c, cudaMemcpy(&acc_total, c->d_counters + 1, sizeof acc_total, cudaMemcpyDeviceToHost));
         info->accepted = (int64_t)acc_total;
-        info->step_launches = (int64_t)n_launch + (int64_t)(demcz_linreg_launches(c) - lin_launch0);
+        info->step_launches = (int64_t)(n_launch + n_launch_untimed) + (int64_t)(demcz_linreg_launches(c) - lin_launch0);
         float ms = 0.f;
         CU(c, cudaEventElapsedTime(&ms, c->ev_run[0], c->ev_run[1]));
         info->device_ms = ms;

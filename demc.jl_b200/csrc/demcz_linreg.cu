@@ -54,6 +54,7 @@ struct demcz_linreg_state {
     double* lp64 = nullptr;                        // [ldx] current log-objective
     double* lphist64 = nullptr;                    // [G][N]
     uint32_t* wacc = nullptr;                      // [ldx] accept word of the pending proposal
+    float* geo = nullptr;                          // [ldx] snooker generations: log Jacobian factor of the pending proposal
     int tile_n = 0, tiles = 0, R = 0, tiles_per_chunk = 0;
     int terms = 3;                                 // 3 MMA terms per product (FP32-equivalent) or 1 (measurement only)
     // kind 1 (default): 2-way FP16 split on tcgen05 kind::f16 — x = hi + lo, both FP16, operands pre-scaled by powers of
@@ -61,6 +62,7 @@ struct demcz_linreg_state {
     // same three products d_lo X_hi + d_hi X_lo + d_hi X_hi at twice the TF32 MMA rate and half the X bytes.
     // kind 0: the 3xTF32 split (fallback when the FP16 path's self-test fails; DEMCZ_LINREG_KIND=tf32 forces it).
     int kind = 1;
+    int link = 0;                                  // 0: Gaussian linear regression, 1: Bernoulli-logit GLM (FP16 kind only)
     __half* Xh = nullptr;                          // [n][2 ppad] row-major: [hi(ppad) | lo(ppad)] of X[:,k] * 2^xexp[k]
     uint32_t* Dh = nullptr;                        // [Npad][ppad] words: [hi pairs (ppad/2) | lo pairs (ppad/2)] of d * 2^(Dexp - xexp)
     int* Dexp = nullptr;                           // [Npad] per-chain exponent
@@ -223,6 +225,8 @@ struct LinArgs {
     const double *b0, *g;
     // trace
     uint32_t *tr_r1, *tr_r2; float *tr_u, *tr_xprop;
+    // snooker generation (see snooker_mvn_kernel in demcz_lib.cu): mode 2 of the prepare kernel; geo = (d-1) log|1 + gamma_s proj|
+    float gamma_s; float* geo;
     // multi-GPU: segment flag words to poll before the first gather (demcz_sync.cuh); need = 0: nothing to wait for
     const unsigned long long* flags; int world, my_rank; unsigned long long need;
 };
@@ -230,7 +234,7 @@ struct LinArgs {
 // Philox draw, archive gather, x' = x + c (Z[r1]-Z[r2]) + eps .* z on the block (src/demcz.jl:174-188), then the
 // GEMM operands: d = x' - b0 split into TF32 hi / lo, and the FP64 linear term d^T g.
 // propose == false: d from the current state (initial log-objective, demcz_eval_logdensity).
-__global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
+__global__ void linreg_prepare_kernel(const LinArgs a, bool propose, bool snooker = false)
 {
     const int chain = blockIdx.x * blockDim.x + threadIdx.x;
     if (a.need != 0ull) {                              // sharded runs: the newest drawable segment has landed from every peer
@@ -241,7 +245,30 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
     const uint32_t cid = a.chain_offset + (uint32_t)chain;
     const uint32_t g_lo = (uint32_t)a.gen, g_hi = (uint32_t)((unsigned long long)a.gen >> 32);
     const float *z1 = nullptr, *z2 = nullptr;
-    if (propose) {
+    float sproj = 0.f;                                 // snooker: gamma_s ((z1 - z2) . e) / (e . e), e = x - z
+    const float* zs = nullptr;
+    if (propose && snooker) {
+        const u32x4 w = philox4x32_10(cid, g_lo, kSnookerCall, g_hi, a.keys);
+        uint32_t z, r1, r2;
+        draw_triple(__umulhi(w.x, a.Mdraw), __umulhi(w.y, a.Mdraw - 1u), __umulhi(w.z, a.Mdraw - 2u), z, r1, r2);
+        float gs = a.gamma_s;
+        if (gs == 0.f) gs = 1.2f + uniform01(philox4x32_10(cid, g_lo, kSnookerCall + 1u, g_hi, a.keys).x);
+        if (a.tr_r1) {
+            const size_t o = ((size_t)(a.grel - 1) * a.nblocks) * a.N + chain;
+            a.tr_r1[o] = r1; a.tr_r2[o] = r2; a.tr_u[o] = uniform01(w.w);
+        }
+        auto phys = [&](uint32_t r) { r += a.zstart; if (r >= a.zcap) r -= a.zcap; return a.Z + (size_t)r * a.ZS; };
+        zs = phys(z); z1 = phys(r1); z2 = phys(r2);
+        float ee = 0.f, num = 0.f;
+        for (int k = 0; k < a.d; ++k) {
+            const float e = a.X[(size_t)k * a.ldx + chain] - zs[k];
+            ee = fmaf(e, e, ee);
+            num = fmaf(z1[k] - z2[k], e, num);
+        }
+        sproj = ee > 0.f ? gs * (num / ee) : 0.f;
+        a.geo[chain] = ee > 0.f ? (float)(a.d - 1) * __logf(fabsf(1.f + sproj)) : -INFINITY;      // x == z: rejected
+        a.wacc[chain] = w.w;
+    } else if (propose) {
         const u32x4 w = philox4x32_10(cid, g_lo, (uint32_t)a.block << 16, g_hi, a.keys);
         uint32_t r1, r2;
         draw_pair(w.x, w.y, a.Mdraw, r1, r2);
@@ -266,7 +293,10 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
 #pragma unroll
         for (int j = 0; j < 8; ++j) x[j] = (k0 + j < a.d) ? a.X[(size_t)(k0 + j) * a.ldx + chain] : 0.f;
         float2 zn[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
-        if (propose) {
+        if (propose && snooker) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) dz[j] = (k0 + j < a.d) ? x[j] - zs[k0 + j] : 0.f;          // e = x - z
+        } else if (propose) {
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
             const float4 a0 = *reinterpret_cast<const float4*>(z1 + k0), b0 = *reinterpret_cast<const float4*>(z2 + k0);
             const float4 a1 = (k0 + 4 < LD4) ? *reinterpret_cast<const float4*>(z1 + k0 + 4) : z;
@@ -283,7 +313,9 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
         for (int j = 0; j < 8; ++j) {
             const int k = k0 + j;
             float xp = x[j];
-            if (propose && k < a.d && a.in_block(k)) {
+            if (propose && snooker) {
+                if (k < a.d) xp = fmaf(sproj, dz[j], x[j]);
+            } else if (propose && k < a.d && a.in_block(k)) {
                 const float2 zz = zn[j >> 1];
                 xp = fmaf(a.cscale, dz[j], fmaf(a.eps[k], (j & 1) ? zz.y : zz.x, x[j]));
             }
@@ -356,7 +388,7 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose)
 struct AccArgs {
     float* X; const float* Xprop; double* lp; const uint32_t* wacc;
     int N, ldx, d, Npad, R;
-    const double *partial, *lin; double ssr0;
+    const double *partial, *lin; double ssr0; int link;
     float T; int tempered;
     long long grel; int block, nblocks; bool last_block;
     // generation bookkeeping (last block only)
@@ -366,6 +398,7 @@ struct AccArgs {
     float* Zw; int ZS; uint32_t append_row0, zcap, chain_offset;
     float* S1; double* S2; const float* shift;
     float* tr_lpprop; uint8_t* tr_acc;
+    const float* geo;             // snooker generation: log of the Jacobian factor (d-1) log(|x'-z| / |x-z|), or nullptr
 };
 
 // log-objective of the proposal from the GEMM partials, tempered Metropolis accept (src/demcz.jl:197-203,
@@ -389,12 +422,13 @@ __global__ void linreg_accept_kernel(const AccArgs a)
 #pragma unroll
             for (int j = 0; j < 16; ++j) if (r0 + j < a.R) q += pr[j];
         }
-        const double lpp = -0.5 * (a.ssr0 - 2.0 * a.lin[chain] + q);
+        const double lpp = a.link ? (a.lin[chain] - q) : -0.5 * (a.ssr0 - 2.0 * a.lin[chain] + q);     // logistic: y.eta - sum softplus(eta)
         const double lp = a.lp[chain];
         if (a.block == 0 && a.lp_gen0) a.lp_gen0[chain] = lp;
         const double logu = log((double)uniform01(a.wacc[chain]));
         const double delta = lpp - lp;
-        const bool acc = a.tempered ? (logu * (double)a.T < delta) : (logu < delta);     // T = 0 -> greedy (Q4); NaN -> reject
+        const double geo = a.geo ? (double)a.geo[chain] : 0.0;
+        const bool acc = a.tempered ? (logu * (double)a.T < delta + (double)a.T * geo) : (logu < delta + geo);     // T = 0 -> greedy (Q4); NaN -> reject
         if (a.tr_lpprop) {
             const size_t o = ((size_t)(a.grel - 1) * a.nblocks + a.block) * a.N + chain;
             a.tr_lpprop[o] = (float)lpp;
@@ -470,13 +504,13 @@ __global__ void linreg_accept_kernel(const AccArgs a)
 }
 
 __global__ void linreg_finish_eval_kernel(const double* __restrict__ partial, const double* __restrict__ lin, int n, int Npad,
-                                          int R, double ssr0, double* __restrict__ out)
+                                          int R, double ssr0, int link, double* __restrict__ out)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double q = 0.0;
     for (int r = 0; r < R; ++r) q += partial[(size_t)r * Npad + i];
-    out[i] = -0.5 * (ssr0 - 2.0 * lin[i] + q);
+    out[i] = link ? (lin[i] - q) : -0.5 * (ssr0 - 2.0 * lin[i] + q);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -676,10 +710,14 @@ struct SsrSmemH {
 };
 
 // TMEM columns: [0, 2 TILE_N) two accumulator stages | d_hi (PPAD/2 columns) | d_lo (PPAD/2 columns)
-template <int PPAD, int TILE_N, int STAGES, int TERMS>
+// LINK selects the per-element function the epilogue sums over the data rows of (X b)[row, chain]:
+//   0: v^2                  Gaussian linear regression (SSR)
+//   1: softplus(eta)        Bernoulli-logit GLM: sum_i log(1 + exp(eta_i)); the y . eta part of the log-likelihood is the
+//                           FP64 linear term b . (X^T y) of the prepare kernel.  MUFU ex2 + lg2 per element.
+template <int PPAD, int TILE_N, int STAGES, int TERMS, int LINK>
 __global__ void __launch_bounds__(kSsrThreads, 1)
 linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* __restrict__ Dh, const int* __restrict__ Dexp,
-                      int ksteps, int tiles, int tiles_per_chunk, int CT, int units, int npad, double* __restrict__ partial)
+                      int ksteps, int tiles, int tiles_per_chunk, int CT, int units, int npad, double* __restrict__ partial, int n_rows)
 {
     using L = SsrSmemH<PPAD, TILE_N, STAGES>;
     constexpr int KBB = L::KBB;
@@ -808,6 +846,7 @@ linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* 
                 if (lane == 0) tc::mbar_arrive(a_full);
             }
             const int fexp = Dexp[chain];
+            const float sc = __int_as_float((127 - fexp) << 23);          // 2^-f (|f| <= 100)
             const int t0 = rc * tiles_per_chunk, t1 = min(tiles, t0 + tiles_per_chunk);
             double accd = 0.0;
             for (int t = t0; t < t1; ++t) {
@@ -823,20 +862,45 @@ linreg_ssr_f16_kernel(const __grid_constant__ CUtensorMap tmXh, const uint32_t* 
                 tc::tc_fence_before();
                 __syncwarp();
                 if (lane == 0) tc::mbar_arrive(&tempty[as]);
-                float2 q[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
+                if constexpr (LINK == 0) {
+                    float2 q[4] = {make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f), make_float2(0.f, 0.f)};
 #pragma unroll
-                for (int j = 0; j < COLS; j += 8) {
+                    for (int j = 0; j < COLS; j += 8) {
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float2 t2 = make_float2(v[j + 2 * e], v[j + 2 * e + 1]);
-                        q[e] = ffma2(t2, t2, q[e]);
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 t2 = make_float2(v[j + 2 * e], v[j + 2 * e + 1]);
+                            q[e] = ffma2(t2, t2, q[e]);
+                        }
                     }
+                    accd += (double)(((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y)));
+                } else {
+                    // softplus(eta) = max(eta, 0) + log1p(exp(-|eta|)), eta = accumulator * 2^-f; rows beyond n (zero-filled by
+                    // TMA, eta = 0 -> ln 2) are masked in the last tile
+                    const int valid = n_rows - (t * TILE_N + half * COLS);
+                    float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
+                    auto sp = [&](float a) {
+                        const float eta = a * sc;
+                        float tt, l2;
+                        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(tt) : "f"(-1.4426950408889634f * fabsf(eta)));
+                        asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l2) : "f"(1.f + tt));
+                        return fmaf(l2, 0.6931471805599453f, fmaxf(eta, 0.f));
+                    };
+                    if (valid >= COLS) {
+#pragma unroll
+                        for (int j = 0; j < COLS; j += 4) { q0 += sp(v[j]); q1 += sp(v[j + 1]); q2 += sp(v[j + 2]); q3 += sp(v[j + 3]); }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < COLS; j += 4) {
+                            q0 += j < valid ? sp(v[j]) : 0.f; q1 += j + 1 < valid ? sp(v[j + 1]) : 0.f;
+                            q2 += j + 2 < valid ? sp(v[j + 2]) : 0.f; q3 += j + 3 < valid ? sp(v[j + 3]) : 0.f;
+                        }
+                    }
+                    accd += (double)((q0 + q1) + (q2 + q3));
                 }
-                accd += (double)(((q[0].x + q[0].y) + (q[1].x + q[1].y)) + ((q[2].x + q[2].y) + (q[3].x + q[3].y)));
                 if (++as == ACC) { as = 0; tph ^= 1; }
             }
-            // undo the chain's power-of-two scale (the accumulators hold (2^f x.d)^2 sums)
-            partial[(size_t)(rc * HALVES + half) * npad + chain] = scalbn(accd, -2 * fexp);
+            // LINK 0: undo the chain's power-of-two scale (the accumulators hold (2^f x.d)^2 sums)
+            partial[(size_t)(rc * HALVES + half) * npad + chain] = LINK == 0 ? scalbn(accd, -2 * fexp) : accd;
         }
     }
 
@@ -896,11 +960,11 @@ int make_map_f16(demcz_ctx* c, CUtensorMap* m, const __half* base, uint64_t rows
     return DEMCZ_OK;
 }
 
-template <int PPAD, int TILE_N, int STAGES, int TERMS>
+template <int PPAD, int TILE_N, int STAGES, int TERMS, int LINK>
 cudaError_t launch_ssr_f16_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
-                             int tiles_per_chunk, int R, int CT, int npad, double* partial)
+                             int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows)
 {
-    auto kern = linreg_ssr_f16_kernel<PPAD, TILE_N, STAGES, TERMS>;
+    auto kern = linreg_ssr_f16_kernel<PPAD, TILE_N, STAGES, TERMS, LINK>;
     constexpr int smem = SsrSmemH<PPAD, TILE_N, STAGES>::TOTAL;
     static bool configured[64] = {false};
     const int dev = c->device & 63;
@@ -911,21 +975,26 @@ cudaError_t launch_ssr_f16_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensor
     }
     const int units = CT * R;
     const int grid = std::min(units, s->sms);
-    kern<<<grid, kSsrThreads, smem, c->stream>>>(tm, dh, dexp, s->ksteps16, tiles, tiles_per_chunk, CT, units, npad, partial);
+    kern<<<grid, kSsrThreads, smem, c->stream>>>(tm, dh, dexp, s->ksteps16, tiles, tiles_per_chunk, CT, units, npad, partial, n_rows);
     return cudaGetLastError();
 }
 
 constexpr int kTileNH = 192;          // data rows per MMA of the FP16 kernel: 2 N + PPAD <= 512 TMEM columns for PPAD = 32 and 64
 
 cudaError_t launch_ssr_f16(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
-                           int tiles_per_chunk, int R, int CT, int npad, double* partial)
+                           int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows = 1 << 30, int link = -1)
 {
+    if (link < 0) link = s->link;
+#define DEMCZ_F16_CASE(PP, ST, TE, LK) return launch_ssr_f16_t<PP, kTileNH, ST, TE, LK>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial, n_rows)
     if (s->ppad == 32) {
-        if (s->terms == 3) return launch_ssr_f16_t<32, kTileNH, 6, 3>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
-        return launch_ssr_f16_t<32, kTileNH, 6, 1>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+        if (link == 1) { if (s->terms == 3) DEMCZ_F16_CASE(32, 6, 3, 1); DEMCZ_F16_CASE(32, 6, 1, 1); }
+        if (s->terms == 3) DEMCZ_F16_CASE(32, 6, 3, 0);
+        DEMCZ_F16_CASE(32, 6, 1, 0);
     }
-    if (s->terms == 3) return launch_ssr_f16_t<64, kTileNH, 4, 3>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
-    return launch_ssr_f16_t<64, kTileNH, 4, 1>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial);
+    if (link == 1) { if (s->terms == 3) DEMCZ_F16_CASE(64, 4, 3, 1); DEMCZ_F16_CASE(64, 4, 1, 1); }
+    if (s->terms == 3) DEMCZ_F16_CASE(64, 4, 3, 0);
+    DEMCZ_F16_CASE(64, 4, 1, 0);
+#undef DEMCZ_F16_CASE
 }
 
 template <int KB, int TILE_N, int STAGES, int TERMS>
@@ -953,7 +1022,7 @@ cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, co
                        const uint32_t* dh = nullptr, const int* dexp = nullptr)
 {
     if (s->kind == 1)
-        return launch_ssr_f16(c, s, s->tmXh, dh ? dh : s->Dh, dexp ? dexp : s->Dexp, s->tiles, s->tiles_per_chunk, s->R, CT, npad, partial);
+        return launch_ssr_f16(c, s, s->tmXh, dh ? dh : s->Dh, dexp ? dexp : s->Dexp, s->tiles, s->tiles_per_chunk, s->R, CT, npad, partial, (int)s->n);
     if (s->ppad == 32) {
         if (s->terms == 3) return launch_ssr_t<1, kTileN32, 4, 3>(c, s, dhi, dlo, CT, npad, partial);
         return launch_ssr_t<1, kTileN32, 4, 1>(c, s, dhi, dlo, CT, npad, partial);
@@ -974,7 +1043,7 @@ void demcz_linreg_free(demcz_ctx* c)
     demcz_linreg_state* s = c->linreg;
     if (!s) return;
     void* ptrs[] = {s->Xhi, s->Xlo, s->d_b0, s->d_g, s->Dhi, s->Dlo, s->Xprop, s->lin, s->partial, s->lp64, s->lphist64, s->wacc,
-                    s->Xh, s->Dh, s->Dexp};
+                    s->Xh, s->Dh, s->Dexp, s->geo};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
     delete s;
@@ -1027,7 +1096,7 @@ static int linreg_f16_selftest(demcz_ctx* c, demcz_linreg_state* s)
     if (e == cudaSuccess && rc == DEMCZ_OK) {
         const int ks_save = s->ksteps16;
         s->ksteps16 = ppad / 16;
-        e = launch_ssr_f16(c, s, tm, dd, de, 1, 1, 1, 1, 128, dp);
+        e = launch_ssr_f16(c, s, tm, dd, de, 1, 1, 1, 1, 128, dp, 1 << 30, 0);
         s->ksteps16 = ks_save;
         if (e == cudaSuccess) e = cudaMemcpyAsync(hp, dp, sizeof hp, cudaMemcpyDeviceToHost, c->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
@@ -1051,7 +1120,19 @@ static int linreg_f16_selftest(demcz_ctx* c, demcz_linreg_state* s)
     return DEMCZ_ERR_UNSUPPORTED;
 }
 
+static int set_likelihood_xb(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y, int link);
+
 extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y)
+{
+    return set_likelihood_xb(c, n, p, X, y, 0);
+}
+
+extern "C" int demcz_set_likelihood_logistic(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y)
+{
+    return set_likelihood_xb(c, n, p, X, y, 1);
+}
+
+static int set_likelihood_xb(demcz_ctx* c, int64_t n, int32_t p, const double* X, const double* y, int link)
 {
     if (!c) return DEMCZ_ERR_INVALID;
     if (c->sticky) return c->sticky;
@@ -1066,7 +1147,9 @@ extern "C" int demcz_set_likelihood_linreg(demcz_ctx* c, int64_t n, int32_t p, c
     demcz_linreg_state* s = new demcz_linreg_state();
     c->linreg = s;
     linreg_init_geometry(s, n, p);
+    s->link = link;
     if (const char* kd = getenv("DEMCZ_LINREG_KIND")) s->kind = (strcmp(kd, "tf32") == 0) ? 0 : 1;
+    if (link == 1 && s->kind != 1) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "the logistic likelihood runs on the FP16 tcgen05 kernel only (DEMCZ_LINREG_KIND=tf32 is set)");
     return linreg_register(c, s, n, p, X, y);
 }
 
@@ -1108,6 +1191,7 @@ static int linreg_register(demcz_ctx* c, demcz_linreg_state* s, int64_t n, int32
     CUL(c, cudaMalloc((void**)&s->partial, (size_t)s->R * (kEpiWarps / 4) * s->Npad * sizeof(double)));
     CUL(c, cudaMalloc((void**)&s->lp64, (size_t)c->ldx * 2 * sizeof(double)));      // [lp | lp at generation start]
     CUL(c, cudaMalloc((void**)&s->wacc, (size_t)c->ldx * sizeof(uint32_t)));
+    CUL(c, cudaMalloc((void**)&s->geo, (size_t)c->ldx * sizeof(float)));
     CUL(c, cudaMemsetAsync(s->lp64, 0, (size_t)c->ldx * 2 * sizeof(double), c->stream));
     if (o.store_chain == 1 && o.Ngeneration / c->thin > 0) CUL(c, cudaMalloc((void**)&s->lphist64, (size_t)(o.Ngeneration / c->thin) * o.N * sizeof(double)));
 
@@ -1160,7 +1244,7 @@ static int linreg_register(demcz_ctx* c, demcz_linreg_state* s, int64_t n, int32
         // OLS by Cholesky of X^T X (host, FP64); a singular Gram matrix falls back to b0 = 0 (still exact, just
         // less well conditioned)
         std::vector<double> Lc((size_t)p * p, 0.0);
-        bool pd = true;
+        bool pd = s->link == 0;                        // the GLM needs eta = X b itself: no centring, b0 = 0 and g = X^T y
         for (int j = 0; j < p && pd; ++j) {
             double d = G[(size_t)j * P1 + j];
             for (int k = 0; k < j; ++k) d -= Lc[(size_t)j * p + k] * Lc[(size_t)j * p + k];
@@ -1216,6 +1300,7 @@ static int linreg_register(demcz_ctx* c, demcz_linreg_state* s, int64_t n, int32
         if (rc == DEMCZ_ERR_UNSUPPORTED) {
             // the FP16 operand layout this library assumes is not what the hardware reads: use the 3xTF32 kernel
             const std::string why = c->err;
+            if (s->link == 1) return demcz_fail(c, DEMCZ_ERR_UNSUPPORTED, "logistic likelihood: %s", why.c_str());
             demcz_linreg_free(c);
             demcz_linreg_state* s2 = new demcz_linreg_state();
             c->linreg = s2;
@@ -1265,7 +1350,7 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
     const int use_npad = npad > s->Npad ? npad : s->Npad;
     if (e == cudaSuccess) e = launch_ssr(c, s, dhi, dlo, npad / 128, use_npad, partial, dh, dexp);
     if (e == cudaSuccess) {
-        linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R * (kEpiWarps / 4), s->ssr0, own_state ? s->lp64 : out_dev);
+        linreg_finish_eval_kernel<<<grid1(n), 256, 0, c->stream>>>(partial, lin, n, use_npad, s->R * (kEpiWarps / 4), s->ssr0, s->link, own_state ? s->lp64 : out_dev);
         e = cudaGetLastError();
     }
     s->ssr_launches++;
@@ -1284,8 +1369,8 @@ std::string demcz_linreg_info(demcz_ctx* c)
     if (!s) return "";
     char buf[512];
     if (s->kind == 1)
-        snprintf(buf, sizeof buf, "linreg_kind=f16;linreg_terms=%d;linreg_kernel=linreg_ssr_f16_kernel<%d,%d> (tcgen05 kind::f16, 2-way FP16 split: %d MMA terms, A in TMEM%s);",
-                 s->terms, s->ppad, kTileNH, s->terms, s->swap_halves ? ", swapped halves" : "");
+        snprintf(buf, sizeof buf, "linreg_kind=f16;linreg_terms=%d;linreg_link=%s;linreg_kernel=linreg_ssr_f16_kernel<%d,%d> (tcgen05 kind::f16, 2-way FP16 split: %d MMA terms, A in TMEM%s%s);",
+                 s->terms, s->link ? "logit" : "gaussian", s->ppad, kTileNH, s->terms, s->swap_halves ? ", swapped halves" : "", s->link ? ", softplus epilogue" : "");
     else
         snprintf(buf, sizeof buf, "linreg_kind=tf32;linreg_terms=%d;linreg_kernel=linreg_ssr_kernel<%d,%d> (tcgen05 kind::tf32, 3xTF32 split, A in TMEM);linreg_fallback=%s;",
                  s->terms, s->ppad / 32, s->tile_n, s->fallback_reason.c_str());
@@ -1310,7 +1395,7 @@ double demcz_linreg_profile_ms(demcz_ctx* c, long long* launches)
 // ------------------------------------------------------------------------------------------------
 // generations [g, g + n_gens) of this context (0-based g), archive frozen; append after the last one if asked
 // ------------------------------------------------------------------------------------------------
-int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half)
+int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, bool acc, int half, bool snooker)
 {
     demcz_linreg_state* s = c->linreg;
     if (!s) return demcz_fail(c, DEMCZ_ERR_INVALID, "linreg likelihood not set");
@@ -1322,7 +1407,8 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
     { int rc = demcz_hist_begin(c, g, n_gens, &hist, &lphist); if (rc != DEMCZ_OK) return rc; }
     for (int gi = 0; gi < n_gens; ++gi) {
         const int64_t grel = g + gi + 1;
-        for (int b = 0; b < o.Nblocks; ++b) {
+        const int nb_run = snooker ? 1 : o.Nblocks;              // a snooker generation is ONE proposal moving all coordinates
+        for (int b = 0; b < nb_run; ++b) {
             LinArgs a;
             memset(&a, 0, sizeof a);
             a.X = c->dX; a.N = o.N; a.ldx = c->ldx; a.d = o.d; a.ppad = s->ppad;
@@ -1343,7 +1429,9 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
             a.flags = demcz_flags(c); a.world = o.world; a.my_rank = o.rank;
             a.need = (gi == 0 && b == 0) ? demcz_comm_need(c) : 0ull;          // once per archive view
-            linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true);
+            a.gamma_s = (float)o.snooker_gamma; a.geo = s->geo;
+            if (snooker && Mdraw < 3) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: the snooker update needs 3 drawable archive rows");
+            linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true, snooker);
             CUL(c, cudaGetLastError());
 
             if (o.profile) {
@@ -1358,10 +1446,11 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
             memset(&q, 0, sizeof q);
             q.X = c->dX; q.Xprop = s->Xprop; q.lp = s->lp64; q.wacc = s->wacc;
             q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R * (kEpiWarps / 4);
-            q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0;
+            q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0; q.link = s->link;
             q.tempered = o.anneal ? 1 : 0;
             q.T = o.anneal ? c->hT[(size_t)grel - 1] : 1.f;
-            q.grel = grel; q.block = b; q.nblocks = o.Nblocks; q.last_block = (b == o.Nblocks - 1);
+            q.grel = grel; q.block = b; q.nblocks = o.Nblocks; q.last_block = (b == nb_run - 1);
+            q.geo = snooker ? s->geo : nullptr;
             q.lp_gen0 = o.Nblocks > 1 ? s->lp64 + c->ldx : nullptr;
             q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
             q.count_run = (grel != 1) ? 1 : 0;

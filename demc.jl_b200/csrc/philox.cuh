@@ -41,6 +41,34 @@ __device__ __forceinline__ u32x4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_
     return u32x4{c0, c1, c2, c3};
 }
 
+// host copy (generation-level decisions such as "is this a snooker generation" are taken by the host from the same stream)
+inline u32x4 philox4x32_10_host(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3, const PhiloxKeys& K)
+{
+    for (int r = 0; r < 10; ++r) {
+        const uint64_t p0 = (uint64_t)kPhiloxM0 * c0, p1 = (uint64_t)kPhiloxM1 * c2;
+        const uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ K.k0[r], n1 = (uint32_t)p1, n2 = (uint32_t)(p0 >> 32) ^ c3 ^ K.k1[r], n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+    }
+    return u32x4{c0, c1, c2, c3};
+}
+
+// Snooker update (ter Braak & Vrugt 2008), stream layout: block field 0xFFFF.
+//   generation-level choice: ctr = (0xFFFFFFFF, gen lo, 0xFFFF0000, gen hi), word 0 -> u; snooker iff u < snooker_prob
+//   per chain: call 0xFFFF0000 -> (w_z, w_z1, w_z2, w_accept), call 0xFFFF0001 -> word 0: jump size gamma_s = 1.2 + u
+// z, z1, z2 are three DISTINCT archive rows: z = mulhi(w_z, M); z1 = j + (j >= z), j = mulhi(w_z1, M-1);
+// z2 = j2 stepped over min(z,z1) and max(z,z1), j2 = mulhi(w_z2, M-2).
+constexpr uint32_t kSnookerCall = 0xFFFF0000u;
+__host__ __device__ __forceinline__ void draw_triple(uint32_t z_hi32, uint32_t z1_hi32, uint32_t z2_hi32, uint32_t& z, uint32_t& z1, uint32_t& z2)
+{
+    // arguments are already the mulhi results: z in [0,M), z1 in [0,M-1), z2 in [0,M-2)
+    z = z_hi32;
+    z1 = z1_hi32 + (z1_hi32 >= z ? 1u : 0u);
+    const uint32_t lo = z < z1 ? z : z1, hi = z < z1 ? z1 : z;
+    z2 = z2_hi32;
+    if (z2 >= lo) ++z2;
+    if (z2 >= hi) ++z2;
+}
+
 // ((w >> 9) + 0.5) * 2^-23 : in (0,1), exact in FP32 (23-bit integer + 1/2)
 __device__ __forceinline__ float uniform01(uint32_t w)
 {

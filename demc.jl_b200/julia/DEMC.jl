@@ -89,6 +89,12 @@ register(ctx, l::MvNormalLogpdf) = ccall((:demcz_set_likelihood_mvnormal, libdem
     (Ptr{Cvoid}, Int32, Ptr{Float64}, Ptr{Float64}, Int32), ctx, length(l.μ), l.μ, l.Σ, l.drop_constant)
 register(ctx, l::LinRegLoglik) = ccall((:demcz_set_likelihood_linreg, libdemcz), Cint,
     (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}), ctx, size(l.X, 1), size(l.X, 2), l.X, l.y)
+struct LogisticLoglik <: GPULikelihood          # sum(y .* (X*b) .- log1p.(exp.(X*b))): Bernoulli-logit GLM (extension)
+    X::Matrix{Float64}
+    y::Vector{Float64}
+end
+register(ctx, l::LogisticLoglik) = ccall((:demcz_set_likelihood_logistic, libdemcz), Cint,
+    (Ptr{Cvoid}, Int64, Int32, Ptr{Float64}, Ptr{Float64}), ctx, size(l.X, 1), size(l.X, 2), l.X, l.y)
 register(ctx, f) = throw(ArgumentError("logobj must be a registered GPU likelihood (MvNormalLogpdf, QuadraticLogobj, LinRegLoglik); closures are not supported and there is no CPU fallback"))
 
 tempbaseline(ig, Ng, T0, TN) = T0 * (TN / T0)^(ig / Ng)          # src/demcz_anneal.jl:1-3

@@ -145,6 +145,11 @@ int demcz_set_likelihood_mvnormal(demcz_ctx* ctx, int32_t d, const double* mu, c
 /* Linreg: -0.5*sum((y .- X*b).^2), test/example_linreg.jl:32.  X: n x p column-major. */
 int demcz_set_likelihood_linreg(demcz_ctx* ctx, int64_t n, int32_t p, const double* X, const double* y);
 
+/* A further descriptor on the same tensor-core contraction (not in the reference, whose users pass any
+ * closure at src/demcz.jl:189): Bernoulli-logit GLM log-likelihood sum_i [y_i eta_i - log(1 + exp(eta_i))], eta = X b,
+ * y_i in {0,1} (any real y is accepted: the y term is linear).  X: n x p column-major. */
+int demcz_set_likelihood_logistic(demcz_ctx* ctx, int64_t n, int32_t p, const double* X, const double* y);
+
 /* replaces: Zmat argument + vcat pre-extension (src/demcz.jl:10-12).  Z: M0 x d column-major. */
 int demcz_set_archive(demcz_ctx* ctx, const double* Z, int64_t M0);
 /* replaces: prevrun state (src/demcz.jl:20-21).  X: N x d col-major; logp: N or NULL (evaluate).

@@ -125,6 +125,17 @@ class LinRegLik:
         return -0.5 * np.sum(R * R, axis=0)
 
 
+class LogisticLik(LinRegLik):
+    """Bernoulli-logit GLM: sum(y*eta - log(1 + exp(eta))), eta = X b.  Not in the reference (which takes any closure,
+    src/demcz.jl:189); textbook formula, evaluated with the overflow-safe logaddexp."""
+
+    kind = 2
+
+    def logdensity(self, B):
+        eta = self.X @ np.atleast_2d(B).T
+        return self.y @ eta - np.sum(np.logaddexp(0.0, eta), axis=0)
+
+
 # ------------------------------------------------------------------------------------------------
 # One generation, all chains, generation-synchronous archive (update_blocks ->
 # update_demcz_chain_block -> accept: src/demcz.jl:167-203; tempered: src/demcz_anneal.jl:142-178)
@@ -167,6 +178,62 @@ def block_update(X, lp, Z, M, lik, block, ib, eps_scale, gamma, seed, gen_abs, T
             acc = np.log(u) < (lpp - lp) / T                               # anneal :173
             margin = (lpp - lp) - T * np.log(u)
     return dict(r1=r1, r2=r2, u=u, xprop=Xp, lp_prop=lpp, accepted=acc, margin=margin)
+
+
+SNOOKER_CALL = 0xFFFF0000
+
+
+def is_snooker_gen(seed, gen_abs, prob):
+    """Generation-level choice of the snooker update: ctr = (0xFFFFFFFF, gen lo, 0xFFFF0000, gen hi), word 0 -> u < prob."""
+    if not prob > 0:
+        return False
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    ctr = np.array([0xFFFFFFFF, gen_abs & 0xFFFFFFFF, SNOOKER_CALL, (gen_abs >> 32) & 0xFFFFFFFF], dtype=np.uint64)
+    return bool(uniform(philox4x32_10(ctr, key)[0]) < prob)
+
+
+def snooker_update(X, lp, Z, M, lik, gamma_s, seed, gen_abs, T=None, chain_offset=0, chain_ids=None, zstart=0, zcap=None):
+    """Snooker update of ter Braak & Vrugt (2008) for every chain — the update the reference's README cites
+    (README.md:57-59) but does not implement; restated from the paper:
+        z, z1, z2: three distinct archive rows; e = x - z;
+        x' = x + gamma_s * e * ((z1 - z2) . e) / (e . e)          (the difference of the projections of z1, z2 on the line x - z)
+        accept with probability min(1, pi(x')/pi(x) * (|x' - z| / |x - z|)^(d-1)),   |x' - z| / |x - z| = |1 + gamma_s proj|
+    gamma_s = 0 -> uniform on [1.2, 2.2] (the paper's choice).  Tempered: log u < Delta/T + (d-1) log(...)."""
+    X = np.asarray(X, dtype=np.float64)
+    lp = np.asarray(lp, dtype=np.float64)
+    N, d = X.shape
+    key = (seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF)
+    cid = (np.arange(N, dtype=np.uint64) if chain_ids is None else np.asarray(chain_ids, dtype=np.uint64)) + np.uint64(chain_offset)
+    ctr = counters(cid, gen_abs, 0, 0)
+    ctr[..., 2] = np.uint64(SNOOKER_CALL)
+    w = philox4x32_10(ctr, key)
+    z = ((w[:, 0].astype(np.uint64) * np.uint64(M)) >> np.uint64(32)).astype(np.int64)
+    j1 = ((w[:, 1].astype(np.uint64) * np.uint64(M - 1)) >> np.uint64(32)).astype(np.int64)
+    z1 = j1 + (j1 >= z)
+    z2 = ((w[:, 2].astype(np.uint64) * np.uint64(M - 2)) >> np.uint64(32)).astype(np.int64)
+    lo, hi = np.minimum(z, z1), np.maximum(z, z1)
+    z2 = z2 + (z2 >= lo)
+    z2 = z2 + (z2 >= hi)
+    if gamma_s == 0:
+        ctr[..., 2] = np.uint64(SNOOKER_CALL + 1)
+        gs = 1.2 + uniform(philox4x32_10(ctr, key)[:, 0])
+        gs = gs.astype(np.float32).astype(np.float64)          # the device forms 1.2f + u in FP32
+    else:
+        gs = np.full(N, float(np.float32(gamma_s)))
+    ph = (lambda r: r) if zcap is None else (lambda r: (r + zstart) % zcap)
+    e = X - Z[ph(z)]
+    ee = np.sum(e * e, axis=1)
+    num = np.sum((Z[ph(z1)] - Z[ph(z2)]) * e, axis=1)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        proj = np.where(ee > 0, gs * num / ee, 0.0)
+        Xp = X + proj[:, None] * e
+        lpp = lik.logdensity(Xp)
+        geo = (d - 1) * np.log(np.abs(1.0 + proj))
+        u = uniform(w[:, 3])
+        Tm = 1.0 if T is None else T
+        margin = (lpp - lp) + Tm * geo - Tm * np.log(u)
+        acc = (ee > 0) & (margin > 0)
+    return dict(z=z, r1=z1, r2=z2, u=u, xprop=Xp, lp_prop=lpp, accepted=acc, margin=margin, geo=geo)
 
 
 def generation(X, lp, Z, M, lik, blocks, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0):

@@ -27,6 +27,8 @@ XPROP_ATOL = 1e-6
 
 
 def oracle_lik(logobj):
+    if isinstance(logobj, DEMC.LogisticLoglik):
+        return orc.LogisticLik(logobj.X, logobj.y)
     if isinstance(logobj, DEMC.LinRegLoglik):
         return orc.LinRegLik(logobj.X, logobj.y)
     return orc.MvNormalLik(logobj.mu, logobj.Sigma, drop_constant=logobj.drop_constant)
@@ -34,7 +36,7 @@ def oracle_lik(logobj):
 
 def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, anneal=False, T0=3.0, TN=1e-3,
                              Ttable=None, gen_offset=0, init_mode="last_N_of_Z", X0=None, device=0, chunks=None,
-                             lp_rtol=LP_RTOL, sync_mode="strict"):
+                             lp_rtol=LP_RTOL, sync_mode="strict", snooker_prob=0.0, snooker_gamma=0.0):
     """Runs G generations on the GPU with trace + history and replays every proposal through the
     numpy oracle.  `chunks`: optional list of max_generations per demcz_run call (exercises resume
     inside one context).  Returns a dict of statistics; raises AssertionError on any mismatch."""
@@ -43,7 +45,7 @@ def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, a
     lik = oracle_lik(logobj)
     s = DEMC.Sampler(logobj, d, N=N, K=K, Ngeneration=G, blockindex=blocks, eps_scale=eps, γ=gamma, anneal=anneal,
                      T0=T0, TN=TN, seed=seed, gen_offset=gen_offset, store_chain=True, init_mode=init_mode,
-                     trace=True, device=device, sync_mode=sync_mode)
+                     trace=True, device=device, sync_mode=sync_mode, snooker_prob=snooker_prob, snooker_gamma=snooker_gamma)
     try:
         s.set_archive(Z0)
         if X0 is not None:
@@ -87,7 +89,7 @@ def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, a
     for j in range(n_app):
         np.testing.assert_array_equal(Z[M0 + N * j: M0 + N * (j + 1)], chain[:, :, K * (j + 1) - 1])
 
-    stats = dict(proposals=0, accepted=0, in_band=0, band_disagree=0, max_lp_relerr=0.0, max_xprop_err=0.0)
+    stats = dict(proposals=0, accepted=0, in_band=0, band_disagree=0, max_lp_relerr=0.0, max_xprop_err=0.0, snooker_gens=0)
     X = X_init.copy()
     lp = lp_init.copy()
     nb = len(blocks)
@@ -97,6 +99,49 @@ def check_run_against_oracle(logobj, Z0, *, N, K, G, blocks, eps, gamma, seed, a
             n_seg = max(n_seg - 1, 0)
         M = M0 + N * n_seg
         T = Tt[g - 1] if anneal else None
+        if orc.is_snooker_gen(seed, gen_offset + g, snooker_prob):
+            # snooker generation (ter Braak & Vrugt 2008): one proposal per chain, all coordinates; trace in block slot 0
+            stats["snooker_gens"] += 1
+            o = orc.snooker_update(X, lp, Z, M, lik, snooker_gamma, seed, gen_offset + g, T=T)
+            assert np.array_equal(tr["r1"][g - 1, 0], o["r1"]) and np.array_equal(tr["r2"][g - 1, 0], o["r2"]), f"snooker z1/z2 mismatch gen {g}"
+            assert np.array_equal(tr["u"][g - 1, 0].astype(np.float64), o["u"]), f"snooker u mismatch gen {g}"
+            g_xp = tr["xprop"][g - 1, 0].T.astype(np.float64)
+            err = np.abs(g_xp - o["xprop"])
+            scale = np.abs(X) + np.abs(Z[o["z"]]) + np.abs(Z[o["r1"]]) + np.abs(Z[o["r2"]])
+            amp = 1.0 + np.abs(o["xprop"] - X).max(axis=1, keepdims=True) / np.maximum(np.abs(X - Z[o["z"]]).max(axis=1, keepdims=True), 1e-30)
+            tol = XPROP_ATOL + 4e-6 * amp * (scale + np.abs(o["xprop"]))          # FP32 dot products: relative error ~d eps of proj
+            assert np.all(err <= tol), f"snooker xprop mismatch gen {g}: max err {err.max():.3e}"
+            ref_lpp = lik.logdensity(g_xp)
+            g_lpp = tr["lp_prop"][g - 1, 0].astype(np.float64)
+            rel = np.abs(g_lpp - ref_lpp) / np.maximum(np.abs(ref_lpp), 1.0)
+            assert np.all(rel <= lp_rtol), f"snooker lp_prop mismatch gen {g}: max rel {rel.max():.3e}"
+            stats["max_lp_relerr"] = max(stats["max_lp_relerr"], float(rel.max()))
+            g_acc = tr["accepted"][g - 1, 0].astype(bool)
+            Tm = 1.0 if T is None else T
+            # geometry factor from the GPU's own proposal: |x' - z| / |x - z|
+            with np.errstate(divide="ignore", invalid="ignore"):
+                rr = np.sqrt(np.sum((g_xp - Z[o["z"]]) ** 2, axis=1) / np.sum((X - Z[o["z"]]) ** 2, axis=1))
+                geo = (d - 1) * np.log(rr)
+                margin = (ref_lpp - lp) + Tm * geo - Tm * np.log(o["u"])
+            band = lp_rtol * np.maximum(np.maximum(np.abs(ref_lpp), np.abs(lp)), 1.0) * 2.0 + 1e-4 * (d - 1) * Tm
+            ref_acc = margin > 0
+            outside = np.abs(margin) > band
+            assert np.array_equal(g_acc[outside], ref_acc[outside]), f"snooker accept decision mismatch outside the band, gen {g}"
+            stats["in_band"] += int((~outside).sum())
+            stats["band_disagree"] += int((g_acc != ref_acc).sum())
+            stats["proposals"] += N
+            stats["accepted"] += int(g_acc.sum())
+            X[g_acc] = g_xp[g_acc]
+            lp[g_acc] = g_lpp[g_acc]
+            for ib in range(1, len(blocks)):
+                assert not tr["accepted"][g - 1, ib].any()
+            np.testing.assert_array_equal(chain[:, :, g - 1], X, err_msg=f"history mismatch gen {g} (snooker)")
+            if isinstance(logobj, DEMC.LinRegLoglik):
+                np.testing.assert_allclose(log_obj[:, g - 1], lp, rtol=2e-7, err_msg=f"log_obj mismatch gen {g}")
+                lp = log_obj[:, g - 1].copy()
+            else:
+                np.testing.assert_array_equal(log_obj[:, g - 1], lp, err_msg=f"log_obj mismatch gen {g}")
+            continue
         for ib, block in enumerate(blocks):
             o = orc.block_update(X, lp, Z, M, lik, block, ib, np.asarray(eps, dtype=np.float32).astype(np.float64),
                                  _f32(gamma, len(block)), seed, gen_offset + g, T=T)

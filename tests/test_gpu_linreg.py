@@ -207,3 +207,55 @@ def test_fp16_split_equals_tf32_split_decisions():
     np.testing.assert_allclose(res["f16"].log_obj[:, 0], res["tf32"].log_obj[:, 0], rtol=2e-6)
     agree = np.mean(np.all(res["f16"].chain[:, :, -1] == res["tf32"].chain[:, :, -1], axis=1))
     assert agree > 0.9                                      # a near-tie may flip a chain; most chains are bit-identical
+
+
+# ---- Bernoulli-logit GLM on the same tcgen05 contraction (softplus epilogue) ------------------------------------------
+def _logit_data(n, p, rng):
+    X = np.ones((n, p)); X[:, 1:] = rng.normal(size=(n, p - 1))
+    beta = rng.normal(size=p) / np.sqrt(p)
+    y = (rng.random(n) < 1.0 / (1.0 + np.exp(-X @ beta))).astype(np.float64)
+    return X, y, beta
+
+
+@pytest.mark.parametrize("n,p", [(1000, 8), (777, 3), (5000, 40), (20000, 64), (193, 5)])
+def test_logistic_eval_vs_fp64(n, p):
+    rng = np.random.default_rng(n + p)
+    X, y, beta = _logit_data(n, p, rng)
+    ref = orc.LogisticLik(X, y)
+    B = np.concatenate([beta + 0.1 * rng.normal(size=(100, p)), np.zeros((1, p)), 3.0 * rng.normal(size=(60, p))])   # near, zero, far (saturated)
+    B = B.astype(np.float32).astype(np.float64)
+    with _sampler(DEMC.LogisticLoglik(X, y)) as s:
+        assert s.kernel_info()["linreg_link"] == "logit"
+        got = s.eval_logdensity(B)
+    want = ref.logdensity(B)
+    rel = np.abs(got - want) / np.abs(want)
+    assert rel.max() < 1e-5, (rel.max(), int(np.argmax(rel)))
+    assert rel[:101].max() < 2e-6, rel[:101].max()        # MUFU ex2 / lg2: ~2e-7 relative per row, unbiased over the rows
+
+
+@pytest.mark.parametrize("n,p,N,blocks", [(1200, 8, 96, None), (900, 10, 70, [[0, 1, 2, 3, 4], [5, 6, 7, 8, 9]])])
+def test_logistic_stepwise(n, p, N, blocks):
+    rng = np.random.default_rng(7)
+    X, y, beta = _logit_data(n, p, rng)
+    Z0 = beta + 0.2 * rng.normal(size=(3 * N, p))
+    st = check_run_against_oracle(DEMC.LogisticLoglik(X, y), Z0, N=N, K=5, G=15, blocks=blocks or [list(range(p))],
+                                  eps=1e-5 * np.ones(p), gamma=2.0, seed=13, snooker_prob=0.2)
+    assert st["accepted"] > 0 and st["max_lp_relerr"] < 2e-6
+
+
+def test_logistic_posterior_is_centred_on_the_mle():
+    rng = np.random.default_rng(17)
+    n, p, N = 4000, 6, 128
+    X, y, beta = _logit_data(n, p, rng)
+    b = np.zeros(p)                                        # Newton iterations for the MLE and the observed information
+    for _ in range(30):
+        mu_ = 1.0 / (1.0 + np.exp(-X @ b))
+        H = X.T @ (X * (mu_ * (1 - mu_))[:, None])
+        b = b + np.linalg.solve(H, X.T @ (y - mu_))
+    Sinv = np.linalg.inv(H)
+    Z0 = b + 2.0 * np.sqrt(np.diag(Sinv)) * rng.normal(size=(3 * N, p))
+    mc, _ = DEMC.demcz_sample(DEMC.LogisticLoglik(X, y), Z0, N, 10, 3000, 1, [list(range(p))], 1e-5 * np.ones(p), 2.38 , verbose=False)
+    m, C = DEMC.mean_cov_chain(mc.chain[:, :, 1500:])
+    sd = np.sqrt(np.diag(Sinv))
+    assert np.all(np.abs(m - b) < 0.15 * sd), (m - b) / sd            # Laplace approximation: mean ~ MLE, cov ~ H^-1
+    assert np.linalg.norm(C - Sinv) / np.linalg.norm(Sinv) < 0.15

@@ -421,3 +421,40 @@ def test_archive_checksum_tracks_the_rows():
     assert hs[0] == hs[1]                                   # same rows, same order -> same checksum (before, after, partial)
     assert hs[0][0] != hs[2][0]                             # position-sensitive
     assert hs[0][0] != hs[0][1] and hs[0][1] != hs[0][2]
+
+
+# ---- snooker update (ter Braak & Vrugt 2008, cited by the reference's README.md:57-59) -----------------
+@pytest.mark.parametrize("d,blocks,anneal,gamma_s", [(5, None, False, 0.0), (10, "two", False, 1.7), (20, None, True, 0.0), (3, None, False, 0.0)])
+def test_snooker_generations_stepwise(d, blocks, anneal, gamma_s):
+    mu, S = example_normpdf_target(d, seed=d)
+    bi = [list(range(d))] if blocks is None else [list(range(0, d // 2)), list(range(d // 2, d))]
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(300, d, seed=d, scale=0.3), N=130, K=4, G=40, blocks=bi,
+                                  eps=1e-5 * np.ones(d), gamma=2.38, seed=21 + d, anneal=anneal, T0=2.0, TN=1e-2,
+                                  snooker_prob=0.35, snooker_gamma=gamma_s, chunks=[7])
+    assert st["snooker_gens"] >= 5 and st["accepted"] > 0
+    assert st["proposals"] == 130 * (st["snooker_gens"] + (40 - st["snooker_gens"]) * len(bi))
+
+
+def test_snooker_linreg_stepwise():
+    rng = np.random.default_rng(31)
+    n, p, N = 1500, 9, 96
+    X = np.ones((n, p)); X[:, 1:] = rng.normal(size=(n, p - 1)); y = X @ (1 + rng.random(p)) + rng.normal(size=n)
+    Z0 = np.linalg.solve(X.T @ X, X.T @ y) + 0.05 * rng.normal(size=(3 * N, p))
+    st = check_run_against_oracle(DEMC.LinRegLoglik(X, y), Z0, N=N, K=5, G=20, blocks=[list(range(p))], eps=1e-5 * np.ones(p),
+                                  gamma=2.0, seed=5, snooker_prob=0.3)
+    assert st["snooker_gens"] >= 3
+
+
+def test_snooker_mixture_samples_the_target():
+    # 10 % snooker generations (the paper's mixture): posterior moments, R-hat and accept band as for the parallel update
+    d, N = 5, 256
+    mu, S = example_normpdf_target(d)
+    mc, Z = DEMC.demcz_sample(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N, 10, 3000, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38,
+                              verbose=False, snooker_prob=0.1, seed=77)
+    keep = mc.chain[:, :, 1500:]
+    b, C = DEMC.mean_cov_chain(keep)
+    sd = np.sqrt(np.diag(S))
+    assert np.all(np.abs(b - mu) < 0.05 * sd)
+    assert np.linalg.norm(C - S) / np.linalg.norm(S) < 0.05
+    ar, Rhat = DEMC.convergence_check(keep, mc.log_obj[:, 1500:], verbose=False)
+    assert np.all(Rhat < 1.01) and 0.1 < ar.mean() < 0.5
