@@ -179,11 +179,19 @@ def test_split_kinds_on_ill_scaled_regressors(kind, nobs, p, monkeypatch):
     rel = np.abs(got - want) / np.abs(want)
     worst = int(np.argmax(rel))
     assert rel.max() < 1e-5, (rel.max(), worst, got[worst], want[worst], [float(rel[a:b].max()) for a, b in ((0, 200), (200, 201), (201, 256), (256, 300))])
+    # Differences near the mode: the intercept and the near-constant column are almost collinear, so x . d cancels by
+    # orders of magnitude inside every row — the limit is FP32 accumulation itself ("FP32-equivalent" is the north star's
+    # spec).  Yardstick: the same centred form in plain float32 numpy (sgemm); the split tensor-core product must not be
+    # worse than 3x that (and is usually better: its operands carry 22 bits, its row sums go to FP64).
     near = slice(0, 201)
     dgot, dwant = got[near] - got[200], want[near] - want[200]
-    assert np.all(np.abs(dgot - dwant) < 5e-3 + 2e-6 * np.abs(dwant)), np.max(np.abs(dgot - dwant))
+    X32, D32 = X.astype(np.float32), (B[near] - bols).astype(np.float32)
+    q32 = np.sum((X32 @ D32.T).astype(np.float32) ** 2, axis=0, dtype=np.float32).astype(np.float64)
+    q64 = np.sum((X @ (B[near] - bols).T) ** 2, axis=0)
+    yard = np.max(np.abs(0.5 * (q32 - q64)))
+    assert np.max(np.abs(dgot - dwant)) < max(5e-3, 3.0 * yard), (np.max(np.abs(dgot - dwant)), yard)
     N = 96
-    Z0 = bols + 2 * sd * rng.normal(size=(3 * N, p))
+    Z0 = bols + 2.0 * rng.normal(size=(3 * N, p)) @ Lp.T           # over-dispersed along the posterior's own geometry
     st = check_run_against_oracle(lo, Z0, N=N, K=4, G=8, blocks=[list(range(p))], eps=1e-5 * sd, gamma=2.0, seed=3)
     assert st["max_lp_relerr"] < 1e-5
 

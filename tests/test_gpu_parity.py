@@ -449,12 +449,12 @@ def test_snooker_mixture_samples_the_target():
     # 10 % snooker generations (the paper's mixture): posterior moments, R-hat and accept band as for the parallel update
     d, N = 5, 256
     mu, S = example_normpdf_target(d)
-    mc, Z = DEMC.demcz_sample(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N, 10, 3000, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38,
+    mc, Z = DEMC.demcz_sample(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N, 10, 6000, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38,
                               verbose=False, snooker_prob=0.1, seed=77)
-    keep = mc.chain[:, :, 1500:]
+    keep = mc.chain[:, :, 2000:]
     b, C = DEMC.mean_cov_chain(keep)
     sd = np.sqrt(np.diag(S))
     assert np.all(np.abs(b - mu) < 0.05 * sd)
     assert np.linalg.norm(C - S) / np.linalg.norm(S) < 0.05
-    ar, Rhat = DEMC.convergence_check(keep, mc.log_obj[:, 1500:], verbose=False)
+    ar, Rhat = DEMC.convergence_check(keep, mc.log_obj[:, 2000:], verbose=False)
     assert np.all(Rhat < 1.01) and 0.1 < ar.mean() < 0.5
