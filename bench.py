@@ -207,7 +207,10 @@ def cpu_run_batched(w, *, chains, gens, archive_rows, seed=31953150):
     (The reference itself evaluates the closure chain by chain: src/demcz.jl:189.)"""
     orc = _oracle()
     if w["kind"] == "linreg":
-        lik = orc.LinRegLik(w["X"], w["y"])
+        class _ChunkedLinReg:                      # same formula as orc.LinRegLik, rows streamed in cache-sized chunks: DGEMM-bound
+            def logdensity(self, B):
+                return _linreg_logdensity_chunked(w, np.atleast_2d(B), rows_per_chunk=512)      # fastest chunk measured (L2-resident residual block)
+        lik = _ChunkedLinReg()
     else:
         lik = orc.MvNormalLik(w["mu"], w["Sigma"], drop_constant=(w["kind"] == "quad"))
     Z = make_archive(w, max(archive_rows, chains), seed=7)
