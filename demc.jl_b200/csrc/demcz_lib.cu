@@ -994,9 +994,6 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             else                        { gb = std::min(gb, w0 + every); }
         }
         if (o.anneal && o.adapt) gb = std::min<int64_t>(gb, (g / o.adapt_every + 1) * (int64_t)o.adapt_every);
-        // opts.moments on the closed-form path: one generation per launch, the state is added to the accumulators
-        // after every launch (exact mean_cov_chain of the full history; the linreg path already runs per generation)
-        if (o.moments && c->lik_kind != DEMCZ_LIK_LINREG) gb = g + 1;
         // snooker generations (opts.snooker_prob) run in their own launch: stop the fused launch in front of the next one
         bool snk = false;
         if (o.snooker_prob > 0.0) {
@@ -1080,6 +1077,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.thin = c->thin; a.hist_phase = (int)(g % c->thin); a.hist_idx0 = (unsigned int)(g / c->thin);
             a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank;
             a.need = demcz_comm_need(c);
+            if (o.moments) { a.mom = c->d_mom; memcpy(a.mom_shift2, c->mom_shift, sizeof a.mom_shift2); }
             c->last_append_by_step_kernel = false;
             if (append && o.world > 1 && c->memop_wait && o.sync_mode == DEMCZ_SYNC_OVERLAP) {
                 a.done_word = (unsigned int*)(c->d_barrier + 4);
@@ -1093,7 +1091,7 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             ++n_launch;
             rc = demcz_hist_end(c, g, n_gens);
             if (rc != DEMCZ_OK) return rc;
-            if (o.moments) { rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
+            if (o.moments) c->mom_gens += n_gens;          // accumulated inside the step kernel (MOM instantiation)
         }
         c->proposals += snk ? (int64_t)o.N : (int64_t)n_gens * o.Nblocks * o.N;        // a snooker generation is one proposal per chain
 

@@ -83,6 +83,11 @@ struct StepArgs {
     const unsigned long long* flags;
     int world, my_rank;
     unsigned long long need;
+    // opts.moments (MOM kernels): streaming first / second moments of EVERY generation of every chain,
+    // mom[k] += sum (x_k - s_k), mom[64 + 64 k1 + k2] += sum (x_k1 - s_k1)(x_k2 - s_k2) for k1 <= k2 (FP64 global
+    // accumulators; s = mom_shift2, fixed for the life of the accumulators)
+    double* mom;
+    float2 mom_shift2[16];
     // appending launches of a sharded run: the last CTA to finish publishes `done_seq` in `done_word` (release, gpu
     // scope) — the side stream waits on that word (stream memory operation) before it moves the rows to the peers,
     // so the compute stream carries nothing but step kernels.  done_word == nullptr: not used.
@@ -236,7 +241,11 @@ __device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ Wc, c
 // rows that straddle a 128-byte line (measured 1.39x the DRAM bytes per row for d = 20), but a rank's appended rows
 // are contiguous, so they cross NVLink as whole lines — the layout of choice when the exchange, not the gather,
 // bounds the K-block (8 GPUs).
-template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false>
+// MOM: per generation every warp stages its 32 x LD tile of (x - shift) in the staging buffer it has just consumed and
+// accumulates the warp's LD x LD cross products in registers: the upper triangle is cut into 4 x 4 blocks, a lane owns
+// one block for a subset of the chains (two LDS.128 + 8 FFMA2 per chain), column sums by lane k < LD.  One flush per
+// launch: registers -> shared (per CTA) -> FP64 atomics.  mean_cov_chain of the full history without the history.
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false, bool MOM = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
@@ -252,6 +261,7 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     __shared__ float red_s2[ACC ? LD : 1];
     __shared__ __align__(16) float2 scW[W_SMEM ? NWC + H : 1];
     __shared__ float2 s2s[S2_SMEM ? H * WARPS * 32 : 1];
+    __shared__ float momG[MOM ? LD * LD + LD : 1];           // CTA-level cross products + column sums
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     float* wbase = smem + warp * (STAGES * SL::FLOATS);
@@ -269,6 +279,7 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     wait_peer_segments(a.flags, a.world, a.my_rank, a.need);
     if (threadIdx.x < 2) red_cnt[threadIdx.x] = 0u;
     if (ACC && threadIdx.x < LD) red_s2[threadIdx.x] = 0.f;
+    if (MOM) for (int t = threadIdx.x; t < LD * LD + LD; t += WARPS * 32) momG[t] = 0.f;
     if (W_SMEM)
         for (int t = threadIdx.x; t < NWC + H; t += WARPS * 32) scW[t] = t < NWC ? P.W[t] : P.mu2[t - NWC];
     __syncthreads();
@@ -344,6 +355,26 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
 
     if (0 < Q) prefetch(0);
     cp_async_commit();
+
+    // ---- MOM: which 4 x 4 block(s) of the upper triangle and which chains this lane accumulates ---------------------
+    constexpr int MB = C * (C + 1) / 2;                                        // blocks
+    constexpr int MS = MB > 16 ? 1 : MB > 8 ? 2 : MB > 4 ? 4 : MB > 2 ? 8 : MB > 1 ? 16 : 32;    // chain splits per block
+    constexpr int MI = (MB * MS + 31) / 32;                                    // blocks per lane (2 only for LD = 32)
+    int mba[MOM ? MI : 1], mbb[MOM ? MI : 1];
+    float2 macc[MOM ? MI * 8 : 1];
+    float msum = 0.f;                                                          // column sum of column `lane` (lane < LD)
+    if (MOM) {
+#pragma unroll
+        for (int it = 0; it < MI; ++it) {
+            const int blk = (lane + 32 * it) / MS;                             // item = (block, split); split = item % MS
+            int aa = 0, rem = blk;                                             // row-major enumeration of a <= b
+            while (aa < C && rem >= C - aa) { rem -= C - aa; ++aa; }
+            mba[it] = blk < MB ? aa : -1;
+            mbb[it] = aa + rem;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) macc[it * 8 + e] = make_float2(0.f, 0.f);
+        }
+    }
 
     // ---- consumer ---------------------------------------------------------------------------
     int cg = 0, cb = 0;
@@ -448,6 +479,46 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
                     else s2[k] = ffma2(t, t, s2[k]);
                 }
             }
+            if (MOM) {
+                // stage (x - shift) of the warp's 32 chains in the buffer consumed above (free until the next iteration's prefetch)
+                float* mt = wbase + (q & 1) * SL::FLOATS;
+                float4* mrow = reinterpret_cast<float4*>(mt + lane * LDS);
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const float2 t0 = active ? fsub2(x2[2 * c], a.mom_shift2[2 * c]) : make_float2(0.f, 0.f);
+                    const float2 t1 = active ? fsub2(x2[2 * c + 1], a.mom_shift2[2 * c + 1]) : make_float2(0.f, 0.f);
+                    mrow[c] = make_float4(t0.x, t0.y, t1.x, t1.y);
+                }
+                __syncwarp();
+                if (lane < LD) {
+#pragma unroll 8
+                    for (int c = 0; c < 32; ++c) msum += mt[c * LDS + lane];
+                }
+#pragma unroll
+                for (int it = 0; it < MI; ++it) {
+                    if (mba[it] >= 0) {
+                        const int split = (lane + 32 * it) % MS;
+                        const float* pa = mt + 4 * mba[it];
+                        const float* pb = mt + 4 * mbb[it];
+#pragma unroll 4
+                        for (int i = 0; i < 32 / MS; ++i) {
+                            const int c = i * MS + split;
+                            const float4 A = *reinterpret_cast<const float4*>(pa + c * LDS);
+                            const float4 B = *reinterpret_cast<const float4*>(pb + c * LDS);
+                            const float2 b01 = make_float2(B.x, B.y), b23 = make_float2(B.z, B.w);
+                            macc[it * 8 + 0] = ffma2(make_float2(A.x, A.x), b01, macc[it * 8 + 0]);
+                            macc[it * 8 + 1] = ffma2(make_float2(A.x, A.x), b23, macc[it * 8 + 1]);
+                            macc[it * 8 + 2] = ffma2(make_float2(A.y, A.y), b01, macc[it * 8 + 2]);
+                            macc[it * 8 + 3] = ffma2(make_float2(A.y, A.y), b23, macc[it * 8 + 3]);
+                            macc[it * 8 + 4] = ffma2(make_float2(A.z, A.z), b01, macc[it * 8 + 4]);
+                            macc[it * 8 + 5] = ffma2(make_float2(A.z, A.z), b23, macc[it * 8 + 5]);
+                            macc[it * 8 + 6] = ffma2(make_float2(A.w, A.w), b01, macc[it * 8 + 6]);
+                            macc[it * 8 + 7] = ffma2(make_float2(A.w, A.w), b23, macc[it * 8 + 7]);
+                        }
+                    }
+                }
+                __syncwarp();                    // the tile is dead: the next iteration may prefetch into it
+            }
             lp_gen0 = lp;
             ++cg;
         }
@@ -494,6 +565,30 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
         if (red_cnt[1]) atomicAdd(a.accepted_total, (unsigned long long)red_cnt[1]);
     }
     if (ACC && threadIdx.x < a.d) atomicAdd(&a.S2[threadIdx.x], (double)red_s2[threadIdx.x]);
+
+    if (MOM) {                                   // registers -> CTA accumulators -> FP64 global (upper triangle, k1 <= k2)
+#pragma unroll
+        for (int it = 0; it < MI; ++it) {
+            if (mba[it] >= 0) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float* g = momG + (4 * mba[it] + i) * LD + 4 * mbb[it];
+                    atomicAdd(g + 0, macc[it * 8 + 2 * i].x); atomicAdd(g + 1, macc[it * 8 + 2 * i].y);
+                    atomicAdd(g + 2, macc[it * 8 + 2 * i + 1].x); atomicAdd(g + 3, macc[it * 8 + 2 * i + 1].y);
+                }
+            }
+        }
+        if (lane < LD) atomicAdd(momG + LD * LD + lane, msum);
+        __syncthreads();
+        for (int t = threadIdx.x; t < LD * LD + LD; t += WARPS * 32) {
+            if (t < LD * LD) {
+                const int k1 = t / LD, k2 = t - k1 * LD;
+                if (k1 <= k2 && k2 < a.d) atomicAdd(a.mom + 64 + 64 * k1 + k2, (double)momG[t]);
+            } else if (t - LD * LD < a.d) {
+                atomicAdd(a.mom + (t - LD * LD), (double)momG[t]);
+            }
+        }
+    }
 
     if (a.done_word) {                           // the __syncthreads above ordered every thread's append stores before this point
         if (threadIdx.x == 0) {

@@ -29,16 +29,27 @@ inline demcz::MvnParams<LD> demcz_make_mvn_params(const demcz_ctx* c, bool jmajo
 }
 
 
-// one launcher per register-width group (LD = 4*ceil(d/4)): {4, 8, 12}, {16, 20}, {24, 28}, {32}
-cudaError_t demcz_launch_step_g0(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
-cudaError_t demcz_launch_step_g1(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
-cudaError_t demcz_launch_step_g2(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
-cudaError_t demcz_launch_step_g3(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+// one launcher per register width (LD = 4*ceil(d/4)), each in its own translation unit
+cudaError_t demcz_launch_step_ld4(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld8(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld12(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld16(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld20(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld24(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld28(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
+cudaError_t demcz_launch_step_ld32(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full);
 
 inline cudaError_t demcz_launch_step(demcz_ctx* c, const demcz::StepArgs& a, bool acc, bool full)
 {
-    if (c->LD <= 12) return demcz_launch_step_g0(c, a, acc, full);
-    if (c->LD <= 20) return demcz_launch_step_g1(c, a, acc, full);
-    if (c->LD <= 28) return demcz_launch_step_g2(c, a, acc, full);
-    return demcz_launch_step_g3(c, a, acc, full);
+    switch (c->LD) {
+        case 4:  return demcz_launch_step_ld4(c, a, acc, full);
+        case 8:  return demcz_launch_step_ld8(c, a, acc, full);
+        case 12: return demcz_launch_step_ld12(c, a, acc, full);
+        case 16: return demcz_launch_step_ld16(c, a, acc, full);
+        case 20: return demcz_launch_step_ld20(c, a, acc, full);
+        case 24: return demcz_launch_step_ld24(c, a, acc, full);
+        case 28: return demcz_launch_step_ld28(c, a, acc, full);
+        case 32: return demcz_launch_step_ld32(c, a, acc, full);
+    }
+    return cudaErrorInvalidValue;
 }

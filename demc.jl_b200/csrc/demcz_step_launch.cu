@@ -1,5 +1,5 @@
 // demcz_step_launch.cu — instantiations and launch of the fused step kernel (demcz_step.cuh).  Compiled once per
-// register-width group (-DDEMCZ_LD_GROUP=0..3) so that the build parallelises: every (LD, ACC, FULL, DENSE)
+// register width (-DDEMCZ_LD=4,8,...,32) so that the build parallelises: every (LD, ACC, FULL, DENSE, MOM)
 // combination is its own kernel.
 #include "demcz_step_host.h"
 #include <cstdlib>
@@ -13,14 +13,15 @@ constexpr int kWarps = 4;
 // production structure of the step kernel (see tools/step_tune.cu and profiles/ for how it was chosen)
 constexpr int kStepOpt = DEMCZ_STEP_OPT;
 
-// resident blocks per SM the register allocation is held to (4 warps per block)
-template <int LD> constexpr int min_blocks() { return LD <= 20 ? 4 : LD <= 28 ? 3 : 2; }
+// resident blocks per SM the register allocation is held to (4 warps per block); the moments variant keeps its
+// cross-product accumulators in registers and runs one block fewer
+template <int LD, bool MOM> constexpr int min_blocks() { return (LD <= 20 ? 4 : LD <= 28 ? 3 : 2) - (MOM ? 1 : 0); }
 
-template <int LD, bool ACC, bool FULL, bool DENSE>
+template <int LD, bool ACC, bool FULL, bool DENSE, bool MOM>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD>(), kStepOpt, DENSE>;
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD, MOM>(), kStepOpt, DENSE, MOM>;
     const size_t smem = (size_t)kWarps * (2 * SL::FLOATS) * sizeof(float);
     static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
     const int dev = c->device & 63;
@@ -46,59 +47,32 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     return cudaLaunchKernelEx(&cfg, kern, a, P);
 }
 
-template <int LD, bool DENSE>
+template <int LD, bool DENSE, bool MOM>
 cudaError_t launch_step_lay(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
-    if (full) return acc ? launch_step_t<LD, true, true, DENSE>(c, a) : launch_step_t<LD, false, true, DENSE>(c, a);
-    return acc ? launch_step_t<LD, true, false, DENSE>(c, a) : launch_step_t<LD, false, false, DENSE>(c, a);
+    if (full) return acc ? launch_step_t<LD, true, true, DENSE, MOM>(c, a) : launch_step_t<LD, false, true, DENSE, MOM>(c, a);
+    return acc ? launch_step_t<LD, true, false, DENSE, MOM>(c, a) : launch_step_t<LD, false, false, DENSE, MOM>(c, a);
 }
 
 template <int LD>
 cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
+    const bool mom = a.mom != nullptr;
     if constexpr (zslot(LD) != LD) {            // dense slots (DEMCZ_XCHG_DENSE_SLOTS) only differ where the slot has padding
-        if (c->ZS == LD) return launch_step_lay<LD, true>(c, a, acc, full);
+        if (c->ZS == LD) return mom ? launch_step_lay<LD, true, true>(c, a, acc, full) : launch_step_lay<LD, true, false>(c, a, acc, full);
     }
-    return launch_step_lay<LD, false>(c, a, acc, full);
+    return mom ? launch_step_lay<LD, false, true>(c, a, acc, full) : launch_step_lay<LD, false, false>(c, a, acc, full);
 }
 
 }  // namespace
 
-#ifndef DEMCZ_LD_GROUP
-#error "compile with -DDEMCZ_LD_GROUP=0..3"
+#ifndef DEMCZ_LD
+#error "compile with -DDEMCZ_LD=4|8|...|32"
 #endif
 
-#if DEMCZ_LD_GROUP == 0
-cudaError_t demcz_launch_step_g0(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
+#define DEMCZ_CAT2(a, b) a##b
+#define DEMCZ_CAT(a, b) DEMCZ_CAT2(a, b)
+cudaError_t DEMCZ_CAT(demcz_launch_step_ld, DEMCZ_LD)(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
-    switch (c->LD) {
-        case 4:  return launch_step_ld<4>(c, a, acc, full);
-        case 8:  return launch_step_ld<8>(c, a, acc, full);
-        case 12: return launch_step_ld<12>(c, a, acc, full);
-    }
-    return cudaErrorInvalidValue;
+    return launch_step_ld<DEMCZ_LD>(c, a, acc, full);
 }
-#elif DEMCZ_LD_GROUP == 1
-cudaError_t demcz_launch_step_g1(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    switch (c->LD) {
-        case 16: return launch_step_ld<16>(c, a, acc, full);
-        case 20: return launch_step_ld<20>(c, a, acc, full);
-    }
-    return cudaErrorInvalidValue;
-}
-#elif DEMCZ_LD_GROUP == 2
-cudaError_t demcz_launch_step_g2(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    switch (c->LD) {
-        case 24: return launch_step_ld<24>(c, a, acc, full);
-        case 28: return launch_step_ld<28>(c, a, acc, full);
-    }
-    return cudaErrorInvalidValue;
-}
-#else
-cudaError_t demcz_launch_step_g3(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
-{
-    return c->LD == 32 ? launch_step_ld<32>(c, a, acc, full) : cudaErrorInvalidValue;
-}
-#endif
