@@ -555,6 +555,8 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
         alloc((void**)&c->dshift, (size_t)o->d * sizeof(float));
     }
     c->thin = o->thin > 1 ? o->thin : 1;
+    // small-N persistent launches: every chain in one CTA of the step kernel, one GPU, padded slots, no streaming moments
+    c->persistent_ok = o->persistent != 0 && o->world == 1 && o->N <= 128 && !o->moments && o->d <= DEMCZ_MAX_DIM && c->ZS == zslot(c->LD);
     if (o->store_chain == 1 && o->Ngeneration / c->thin > 0) {
         alloc((void**)&c->dhist, (size_t)(o->Ngeneration / c->thin) * o->d * o->N * sizeof(float));
         alloc((void**)&c->dlphist, (size_t)(o->Ngeneration / c->thin) * o->N * sizeof(float));
@@ -982,7 +984,10 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
     int64_t g = g_begin;
     while (g < g_end && !stopped) {
         // ---- next boundary ---------------------------------------------------------------------
-        int64_t gb = std::min<int64_t>(g_end, (g / o.K + 1) * (int64_t)o.K);            // archive append
+        // small-N persistent launches: one CTA holds every chain, the append is a CTA barrier inside the kernel, so the
+        // launch need not end at a K boundary (it still ends at every host decision: Rhat halves, adaptγ, snooker)
+        const bool pers = c->persistent_ok && c->lik_kind == DEMCZ_LIK_MVN;
+        int64_t gb = pers ? g_end : std::min<int64_t>(g_end, (g / o.K + 1) * (int64_t)o.K);            // archive append
         bool acc = false;
         int half = 0;
         if (o.autostop) {
@@ -1000,8 +1005,18 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             if (demcz_is_snooker_gen(c, o.gen_offset + g + 1)) { snk = true; gb = g + 1; }
             else for (int64_t t = g + 1; t < gb; ++t) if (demcz_is_snooker_gen(c, o.gen_offset + t + 1)) { gb = t; break; }
         }
+        if (pers) {
+            // no ring wrap inside a launch, at most 2^15 generations per launch (32-bit proposal counters)
+            gb = std::min<int64_t>(gb, g + 32768);
+            const int64_t room = (c->zcap - c->M) / o.N_global - 2;              // appends that fit well before the ring wraps (the view's wrap rules never apply)
+            const int64_t last = (g / o.K + std::max<int64_t>(room, 0)) * (int64_t)o.K;     // last generation whose append still fits
+            if (last <= g) gb = std::min<int64_t>(gb, (g / o.K + 1) * (int64_t)o.K);       // ring about to wrap: one K-block per launch
+            else gb = std::min<int64_t>(gb, last);
+        }
         const int n_gens = (int)(gb - g);
-        const bool append = (gb % o.K) == 0;
+        const int64_t n_appends = gb / o.K - g / o.K;                            // appends made by this launch (pers: possibly several)
+        const bool pers_launch = pers && !snk && c->M + (n_appends + 2) * o.N_global <= c->zcap;
+        const bool append = pers_launch ? n_appends > 0 : (gb % o.K) == 0;
 
         if (c->lik_kind == DEMCZ_LIK_LINREG) {
             rc = demcz_linreg_generations(c, g, n_gens, append, acc, half, snk);
@@ -1078,6 +1093,12 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
             a.flags = c->dZ ? demcz_flags(c) : nullptr; a.world = o.world; a.my_rank = o.rank;
             a.need = demcz_comm_need(c);
             if (o.moments) { a.mom = c->d_mom; memcpy(a.mom_shift2, c->mom_shift, sizeof a.mom_shift2); }
+            if (pers_launch) {
+                a.pers_K = o.K; a.pers_kphase = (int)(g % o.K);
+                a.pers_delay = (o.sync_mode == DEMCZ_SYNC_OVERLAP && c->appends == 0) ? 1 : 0;
+                // overlap mode: the view handed over by demcz_archive_view already hides the newest segment; every further
+                // append of the launch reveals the one before it
+            }
             c->last_append_by_step_kernel = false;
             if (append && o.world > 1 && c->memop_wait && o.sync_mode == DEMCZ_SYNC_OVERLAP) {
                 a.done_word = (unsigned int*)(c->d_barrier + 4);
@@ -1097,8 +1118,10 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
 
         // ---- archive append + exchange (src/demcz.jl:88-91; sync mode :129-137) -----------------
         if (append) {
-            rc = demcz_archive_appended(c);
-            if (rc != DEMCZ_OK) return rc;
+            for (int64_t t = 0; t < (pers_launch ? n_appends : 1); ++t) {
+                rc = demcz_archive_appended(c);
+                if (rc != DEMCZ_OK) return rc;
+            }
         }
         g = gb;
         c->g_done = g;

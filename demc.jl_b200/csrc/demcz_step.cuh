@@ -83,6 +83,10 @@ struct StepArgs {
     const unsigned long long* flags;
     int world, my_rank;
     unsigned long long need;
+    // small-N persistent launches (PERS kernels, one CTA, world = 1): the launch spans several K-blocks; after every
+    // generation g with (kphase + g) % K == 0 the CTA appends its rows, synchronises and the drawable view grows by N
+    // rows (from the pers_delay-th append of the launch on: overlap sync mode hides the newest segment)
+    int pers_K, pers_kphase, pers_delay;
     // opts.moments (MOM kernels): streaming first / second moments of EVERY generation of every chain,
     // mom[k] += sum (x_k - s_k), mom[64 + 64 k1 + k2] += sum (x_k1 - s_k1)(x_k2 - s_k2) for k1 <= k2 (FP64 global
     // accumulators; s = mom_shift2, fixed for the life of the accumulators)
@@ -245,7 +249,10 @@ __device__ __forceinline__ float mvn_logdensity(const float2* __restrict__ Wc, c
 // accumulates the warp's LD x LD cross products in registers: the upper triangle is cut into 4 x 4 blocks, a lane owns
 // one block for a subset of the chains (two LDS.128 + 8 FFMA2 per chain), column sums by lane k < LD.  One flush per
 // launch: registers -> shared (per CTA) -> FP64 atomics.  mean_cov_chain of the full history without the history.
-template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false, bool MOM = false>
+// PERS: one CTA holds all chains (N <= WARPS * 32) and runs every K-block between two host decisions in ONE launch:
+// the append is a store + __syncthreads instead of a kernel boundary (13 us of launch latency per 10 generations at
+// N = 100 otherwise).  The gather pipeline drains at every append (the next draw needs the grown archive).
+template <int LD, bool ACC, bool FULL, int WARPS, int MINB, int OPT, bool DENSE = false, bool MOM = false, bool PERS = false>
 __global__ void __launch_bounds__(WARPS * 32, MINB)
 demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant__ MvnParams<LD> P)
 {
@@ -319,13 +326,15 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     const bool pact = lpiece < C && lrow < RPI;         // (dense slots) 32 % CP lanes have no piece
     const int soff = (IDX_VEC ? lrow * RPL : lrow) * LDS + lpiece * 4;
     int pg = 0, pb = 0;
+    uint32_t mdraw_cur = a.Mdraw;                       // PERS: grows by N at the launch's appends
+    int pers_appends = 0;
     auto prefetch = [&](int stage) {
         float* st = wbase + stage * SL::FLOATS;
         uint32_t* idx = reinterpret_cast<uint32_t*>(st + SL::ROWS);
         const long long g = a.gen0 + pg;
         const u32x4 w = philox4x32_10(cid, (uint32_t)g, (uint32_t)pb << 16, (uint32_t)((unsigned long long)g >> 32), a.keys);
         uint32_t r1, r2;
-        draw_pair(w.x, w.y, a.Mdraw, r1, r2);
+        draw_pair(w.x, w.y, PERS ? mdraw_cur : a.Mdraw, r1, r2);
         r1 += a.zstart; if (r1 >= a.zcap) r1 -= a.zcap;
         r2 += a.zstart; if (r2 >= a.zcap) r2 -= a.zcap;
         idx[lane] = r1;
@@ -380,7 +389,9 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
     int cg = 0, cb = 0;
     float lp_gen0 = lp;
     for (int q = 0; q < Q; ++q) {
-        if (q + 1 < Q) prefetch((q + 1) & 1);
+        // PERS: the proposal after an append boundary is prefetched behind the barrier below, not here
+        const bool pers_boundary = PERS && (FULL || cb == nb - 1) && ((a.pers_kphase + cg + 1) % a.pers_K == 0);
+        if (q + 1 < Q && !pers_boundary) prefetch((q + 1) & 1);
         cp_async_commit();                       // (possibly empty) keeps the group count uniform
         cp_async_wait<1>();
         __syncwarp();
@@ -521,6 +532,21 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             }
             lp_gen0 = lp;
             ++cg;
+            if (PERS && pers_boundary) {         // append (src/demcz.jl:88-91), make it visible to the CTA, grow the view
+                if (active) {
+                    uint32_t row = a.append_row0 + (uint32_t)pers_appends * (uint32_t)a.N + a.chain_offset + (uint32_t)chain;
+                    float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * ZS);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) dst[c] = make_float4(x2[2 * c].x, x2[2 * c].y, x2[2 * c + 1].x, x2[2 * c + 1].y);
+                    if (C % 2 == 1 && C < CP) dst[C] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                ++pers_appends;
+                __threadfence_block();
+                __syncthreads();
+                if (pers_appends > a.pers_delay) mdraw_cur += (uint32_t)a.N;
+                if (q + 1 < Q) prefetch((q + 1) & 1);
+                cp_async_commit();
+            }
         }
     }
 
@@ -531,7 +557,7 @@ demcz_step_mvn_kernel(const __grid_constant__ StepArgs a, const __grid_constant_
             if (k < a.d) a.X[(size_t)k * a.ldx + chain] = (k & 1) ? x2[k / 2].y : x2[k / 2].x;
         a.logp[chain] = lp;
         if (a.chain_changed) a.chain_changed[chain] += cnt_run;
-        if (a.Zw) {                              // Zmat[M+1,:] .= Xcurrent[ic,:]  (src/demcz.jl:88-91)
+        if (!PERS && a.Zw) {                     // Zmat[M+1,:] .= Xcurrent[ic,:]  (src/demcz.jl:88-91)
             uint32_t row = a.append_row0 + a.chain_offset + (uint32_t)chain;
             if (row >= a.zcap) row -= a.zcap;
             float4* dst = reinterpret_cast<float4*>(a.Zw + (size_t)row * ZS);

@@ -17,11 +17,11 @@ constexpr int kStepOpt = DEMCZ_STEP_OPT;
 // cross-product accumulators in registers and runs one block fewer
 template <int LD, bool MOM> constexpr int min_blocks() { return (LD <= 20 ? 4 : LD <= 28 ? 3 : 2) - (MOM ? 1 : 0); }
 
-template <int LD, bool ACC, bool FULL, bool DENSE, bool MOM>
+template <int LD, bool ACC, bool FULL, bool DENSE, bool MOM, bool PERS = false>
 cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
 {
     using SL = StageLayout<LD>;
-    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD, MOM>(), kStepOpt, DENSE, MOM>;
+    auto kern = demcz_step_mvn_kernel<LD, ACC, FULL, kWarps, min_blocks<LD, MOM>(), kStepOpt, DENSE, MOM, PERS>;
     const size_t smem = (size_t)kWarps * (2 * SL::FLOATS) * sizeof(float);
     static bool configured[64] = {false};       // per instantiation and per device (function attributes are per device)
     const int dev = c->device & 63;
@@ -58,6 +58,10 @@ template <int LD>
 cudaError_t launch_step_ld(demcz_ctx* c, const StepArgs& a, bool acc, bool full)
 {
     const bool mom = a.mom != nullptr;
+    if (a.pers_K > 0) {                         // small-N persistent launch (one CTA; padded slots, no moments: demcz_run arranges that)
+        if (full) return acc ? launch_step_t<LD, true, true, false, false, true>(c, a) : launch_step_t<LD, false, true, false, false, true>(c, a);
+        return acc ? launch_step_t<LD, true, false, false, false, true>(c, a) : launch_step_t<LD, false, false, false, false, true>(c, a);
+    }
     if constexpr (zslot(LD) != LD) {            // dense slots (DEMCZ_XCHG_DENSE_SLOTS) only differ where the slot has padding
         if (c->ZS == LD) return mom ? launch_step_lay<LD, true, true>(c, a, acc, full) : launch_step_lay<LD, true, false>(c, a, acc, full);
     }

@@ -458,3 +458,53 @@ def test_snooker_mixture_samples_the_target():
     assert np.linalg.norm(C - S) / np.linalg.norm(S) < 0.05
     ar, Rhat = DEMC.convergence_check(keep, mc.log_obj[:, 2000:], verbose=False)
     assert np.all(Rhat < 1.01) and 0.1 < ar.mean() < 0.5
+
+
+# ---- small-N persistent launches (opts.persistent): every K-block between two host decisions in ONE launch ----------
+@pytest.mark.parametrize("case", ["plain", "blocks", "anneal_adapt", "rhat", "overlap", "chunks", "tiny_ring", "snooker"])
+def test_persistent_small_n_launches_are_bit_identical_to_one_launch_per_kblock(case):
+    d, N, K, G = 5, 100, 10, 97
+    mu, S = example_normpdf_target(d)
+    kw = dict(K=K, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.38, seed=5, store_chain=True, trace=True)
+    chunks = []
+    if case == "blocks":
+        kw["blockindex"] = [[0, 2, 4], [1, 3]]
+    elif case == "anneal_adapt":
+        kw.update(anneal=True, T0=2.0, TN=1e-3, adapt=True, adapt_every=25)
+    elif case == "rhat":
+        kw.update(autostop=True, autostop_every=30, autostop_Rhat=0.0)
+    elif case == "overlap":
+        kw.update(sync_mode="overlap")
+    elif case == "chunks":
+        chunks = [7, 33, 1]
+    elif case == "tiny_ring":
+        kw.update(archive_capacity=6 * N)             # the ring wraps during the run: persistent launches fall back near the wrap
+    elif case == "snooker":
+        kw.update(snooker_prob=0.2)
+    out = {}
+    for pers in (False, True):
+        with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, persistent=pers, **kw) as s:
+            s.set_archive(_z0(3 * N, d, scale=0.3))
+            for c in chunks:
+                s.run(c)
+            info = s.run()
+            assert s.kernel_info()["step_persistent"] == int(pers)
+            out[pers] = (s.get_state(), s.get_chain(), s.get_archive(), s.get_trace(), s.get_accept_counts(), info)
+    a, b = out[False], out[True]
+    np.testing.assert_array_equal(a[0][0], b[0][0]); np.testing.assert_array_equal(a[0][1], b[0][1])
+    np.testing.assert_array_equal(a[1][0], b[1][0]); np.testing.assert_array_equal(a[1][1], b[1][1])
+    np.testing.assert_array_equal(a[2], b[2])
+    for k in a[3]:
+        np.testing.assert_array_equal(a[3][k], b[3][k], err_msg=k)
+    np.testing.assert_array_equal(a[4], b[4])
+    assert a[5]["accepted"] == b[5]["accepted"] and a[5]["final_gamma"] == b[5]["final_gamma"] and a[5]["M"] == b[5]["M"]
+    if case not in ("tiny_ring",):
+        assert b[5]["step_launches"] < a[5]["step_launches"]          # fewer, longer launches
+
+
+def test_persistent_path_stepwise_against_oracle():
+    d, N = 5, 100                                            # BASELINE config 1 (test/example_normpdf.jl shape)
+    mu, S = example_normpdf_target(d)
+    st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N=N, K=10, G=60, blocks=[list(range(d))],
+                                  eps=1e-5 * np.ones(d), gamma=2.38, seed=31953150)
+    assert st["accepted"] > 0
