@@ -74,7 +74,8 @@ typedef struct {
     int32_t d;                  /* Npar */
     const int32_t* block_ptr;   /* CSR of blockindex: Nblocks+1 offsets ...               */
     const int32_t* block_idx;   /* ... into 0-based column indices (blockindex[ib] .- 1)   */
-    const double* eps_scale;    /* d */
+    const double* eps_scale;    /* d.  The jitter eps_scale .* randn (src/demcz.jl:184,186) is drawn with a 16-bit Box-Muller
+                                   (|z| <= 4.86, 2^16 levels): meant for the reference's eps_scale ~ 1e-5, not as the main proposal noise */
     double gamma;               /* γ */
     double T0, TN;              /* annealing end points (only used to build the default table) */
     int32_t anneal;             /* 0: demcz_sample semantics, 1: demcz_anneal semantics */
