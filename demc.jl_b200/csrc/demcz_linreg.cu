@@ -68,6 +68,10 @@ struct demcz_linreg_state {
     int* Dexp = nullptr;                           // [Npad] per-chain exponent
     int xexp[64] = {0};                            // per-column exponent
     int swap_halves = 0;                           // which half of a 32-bit TMEM column holds the even K element (probed)
+    // the two half-populations are pipelined: the latency-bound prepare / accept kernels of one half run under the GEMM of
+    // the other (two side streams, forked from and joined to the context's stream once per demcz_linreg_generations call)
+    cudaStream_t hstream[2] = {nullptr, nullptr};
+    cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
     std::string fallback_reason;                   // why kind 1 was not used (self-test message), if it was asked for
     CUtensorMap tmXh;
     CUtensorMap tmXhi, tmXlo;
@@ -210,6 +214,7 @@ __global__ void resid_kernel(const double* __restrict__ X, const double* __restr
 struct LinArgs {
     // state
     float* X; int N, ldx, d, ppad;
+    int chain_lo, chain_hi;       // this launch handles chains [chain_lo, chain_hi) (the two half-populations are pipelined)
     uint32_t chain_offset;
     const float* Z; int ZS; uint32_t Mdraw, zstart, zcap;
     long long gen, grel;          // absolute / context-relative generation of this proposal
@@ -236,12 +241,12 @@ struct LinArgs {
 // propose == false: d from the current state (initial log-objective, demcz_eval_logdensity).
 __global__ void linreg_prepare_kernel(const LinArgs a, bool propose, bool snooker = false)
 {
-    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
+    const int chain = a.chain_lo + blockIdx.x * blockDim.x + threadIdx.x;
     if (a.need != 0ull) {                              // sharded runs: the newest drawable segment has landed from every peer
         wait_peer_segments(a.flags, a.world, a.my_rank, a.need);
         __syncthreads();
     }
-    if (chain >= a.N) return;
+    if (chain >= a.chain_hi) return;
     const uint32_t cid = a.chain_offset + (uint32_t)chain;
     const uint32_t g_lo = (uint32_t)a.gen, g_hi = (uint32_t)((unsigned long long)a.gen >> 32);
     const float *z1 = nullptr, *z2 = nullptr;
@@ -388,6 +393,7 @@ __global__ void linreg_prepare_kernel(const LinArgs a, bool propose, bool snooke
 struct AccArgs {
     float* X; const float* Xprop; double* lp; const uint32_t* wacc;
     int N, ldx, d, Npad, R;
+    int chain_lo, chain_hi;
     const double *partial, *lin; double ssr0; int link;
     float T; int tempered;
     long long grel; int block, nblocks; bool last_block;
@@ -410,8 +416,8 @@ __global__ void linreg_accept_kernel(const AccArgs a)
     if (threadIdx.x < 2) red[threadIdx.x] = 0;
     if (threadIdx.x < 64) red_s2[threadIdx.x] = 0.0;
     __syncthreads();
-    const int chain = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = chain < a.N;
+    const int chain = a.chain_lo + blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = chain < a.chain_hi;
     int acc_i = 0, win_i = 0;
     if (active) {
         double q = 0.0;
@@ -962,7 +968,7 @@ int make_map_f16(demcz_ctx* c, CUtensorMap* m, const __half* base, uint64_t rows
 
 template <int PPAD, int TILE_N, int STAGES, int TERMS, int LINK>
 cudaError_t launch_ssr_f16_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
-                             int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows)
+                             int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows, cudaStream_t st)
 {
     auto kern = linreg_ssr_f16_kernel<PPAD, TILE_N, STAGES, TERMS, LINK>;
     constexpr int smem = SsrSmemH<PPAD, TILE_N, STAGES>::TOTAL;
@@ -975,17 +981,19 @@ cudaError_t launch_ssr_f16_t(demcz_ctx* c, demcz_linreg_state* s, const CUtensor
     }
     const int units = CT * R;
     const int grid = std::min(units, s->sms);
-    kern<<<grid, kSsrThreads, smem, c->stream>>>(tm, dh, dexp, s->ksteps16, tiles, tiles_per_chunk, CT, units, npad, partial, n_rows);
+    kern<<<grid, kSsrThreads, smem, st>>>(tm, dh, dexp, s->ksteps16, tiles, tiles_per_chunk, CT, units, npad, partial, n_rows);
     return cudaGetLastError();
 }
 
 constexpr int kTileNH = 192;          // data rows per MMA of the FP16 kernel: 2 N + PPAD <= 512 TMEM columns for PPAD = 32 and 64
 
 cudaError_t launch_ssr_f16(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMap& tm, const uint32_t* dh, const int* dexp, int tiles,
-                           int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows = 1 << 30, int link = -1)
+                           int tiles_per_chunk, int R, int CT, int npad, double* partial, int n_rows = 1 << 30, int link = -1,
+                           cudaStream_t st = nullptr)
 {
     if (link < 0) link = s->link;
-#define DEMCZ_F16_CASE(PP, ST, TE, LK) return launch_ssr_f16_t<PP, kTileNH, ST, TE, LK>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial, n_rows)
+    if (!st) st = c->stream;
+#define DEMCZ_F16_CASE(PP, ST, TE, LK) return launch_ssr_f16_t<PP, kTileNH, ST, TE, LK>(c, s, tm, dh, dexp, tiles, tiles_per_chunk, R, CT, npad, partial, n_rows, st)
     if (s->ppad == 32) {
         if (link == 1) { if (s->terms == 3) DEMCZ_F16_CASE(32, 6, 3, 1); DEMCZ_F16_CASE(32, 6, 1, 1); }
         if (s->terms == 3) DEMCZ_F16_CASE(32, 6, 3, 0);
@@ -998,7 +1006,7 @@ cudaError_t launch_ssr_f16(demcz_ctx* c, demcz_linreg_state* s, const CUtensorMa
 }
 
 template <int KB, int TILE_N, int STAGES, int TERMS>
-cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial)
+cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial, cudaStream_t st)
 {
     auto kern = linreg_ssr_kernel<KB, TILE_N, STAGES, TERMS>;
     constexpr int smem = SsrSmem<KB, TILE_N, STAGES>::TOTAL;
@@ -1011,7 +1019,7 @@ cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, 
     }
     const int units = CT * s->R;
     const int grid = std::min(units, s->sms);
-    kern<<<grid, kSsrThreads, smem, c->stream>>>(s->tmXhi, s->tmXlo, dhi, dlo, s->ppad, s->ksteps, s->tiles, s->tiles_per_chunk, CT,
+    kern<<<grid, kSsrThreads, smem, st>>>(s->tmXhi, s->tmXlo, dhi, dlo, s->ppad, s->ksteps, s->tiles, s->tiles_per_chunk, CT,
                                                  units, npad, partial);
     return cudaGetLastError();
 }
@@ -1019,16 +1027,17 @@ cudaError_t launch_ssr_t(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, 
 constexpr int kTileN32 = 192, kTileN64 = 128;     // data rows per MMA (N) for p <= 32 / p <= 64: 2 N + chain-tile columns <= 512 TMEM columns
 
 cudaError_t launch_ssr(demcz_ctx* c, demcz_linreg_state* s, const float* dhi, const float* dlo, int CT, int npad, double* partial,
-                       const uint32_t* dh = nullptr, const int* dexp = nullptr)
+                       const uint32_t* dh = nullptr, const int* dexp = nullptr, cudaStream_t st = nullptr)
 {
+    if (!st) st = c->stream;
     if (s->kind == 1)
-        return launch_ssr_f16(c, s, s->tmXh, dh ? dh : s->Dh, dexp ? dexp : s->Dexp, s->tiles, s->tiles_per_chunk, s->R, CT, npad, partial, (int)s->n);
+        return launch_ssr_f16(c, s, s->tmXh, dh ? dh : s->Dh, dexp ? dexp : s->Dexp, s->tiles, s->tiles_per_chunk, s->R, CT, npad, partial, (int)s->n, -1, st);
     if (s->ppad == 32) {
-        if (s->terms == 3) return launch_ssr_t<1, kTileN32, 4, 3>(c, s, dhi, dlo, CT, npad, partial);
-        return launch_ssr_t<1, kTileN32, 4, 1>(c, s, dhi, dlo, CT, npad, partial);
+        if (s->terms == 3) return launch_ssr_t<1, kTileN32, 4, 3>(c, s, dhi, dlo, CT, npad, partial, st);
+        return launch_ssr_t<1, kTileN32, 4, 1>(c, s, dhi, dlo, CT, npad, partial, st);
     }
-    if (s->terms == 3) return launch_ssr_t<2, kTileN64, 3, 3>(c, s, dhi, dlo, CT, npad, partial);
-    return launch_ssr_t<2, kTileN64, 3, 1>(c, s, dhi, dlo, CT, npad, partial);
+    if (s->terms == 3) return launch_ssr_t<2, kTileN64, 3, 3>(c, s, dhi, dlo, CT, npad, partial, st);
+    return launch_ssr_t<2, kTileN64, 3, 1>(c, s, dhi, dlo, CT, npad, partial, st);
 }
 
 inline int grid1(long long n, int t = 256) { return (int)((n + t - 1) / t); }
@@ -1046,6 +1055,8 @@ void demcz_linreg_free(demcz_ctx* c)
                     s->Xh, s->Dh, s->Dexp, s->geo};
     for (void* p : ptrs) if (p) cudaFree(p);
     for (cudaEvent_t e : s->ev) cudaEventDestroy(e);
+    for (int h = 0; h < 2; ++h) { if (s->hstream[h]) cudaStreamDestroy(s->hstream[h]); if (s->ev_join[h]) cudaEventDestroy(s->ev_join[h]); }
+    if (s->ev_fork) cudaEventDestroy(s->ev_fork);
     delete s;
     c->linreg = nullptr;
 }
@@ -1343,6 +1354,7 @@ int demcz_linreg_eval(demcz_ctx* c, const float* X, int n, int ldx, double* out_
     LinArgs a;
     memset(&a, 0, sizeof a);
     a.X = const_cast<float*>(X); a.N = n; a.ldx = ldx; a.d = c->o.d; a.ppad = s->ppad;
+    a.chain_lo = 0; a.chain_hi = n;
     a.Dhi = dhi; a.Dlo = dlo; a.lin = lin; a.b0 = s->d_b0; a.g = s->d_g;
     a.kind = s->kind; a.Dh = dh; a.Dexp = dexp; memcpy(a.xexp, s->xexp, sizeof a.xexp); a.swap_halves = s->swap_halves;
     linreg_prepare_kernel<<<grid1(n, 128), 128, 0, c->stream>>>(a, false);
@@ -1405,67 +1417,100 @@ int demcz_linreg_generations(demcz_ctx* c, int64_t g, int n_gens, bool append, b
     { int rc = demcz_archive_view(c, &Mdraw, &zstart); if (rc != DEMCZ_OK) return rc; }
     float* hist = nullptr; void* lphist = nullptr;
     { int rc = demcz_hist_begin(c, g, n_gens, &hist, &lphist); if (rc != DEMCZ_OK) return rc; }
+    if (snooker && Mdraw < 3) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: the snooker update needs 3 drawable archive rows");
+
+    // Two half-populations (split at a multiple of the 128-chain MMA tile), each on its own stream: prepare / accept of
+    // one half run under the GEMM of the other.  Chains are independent while the archive is frozen and every per-chain
+    // sum keeps its order, so the result is bit-identical to one stream.  Not split: a single chain tile, per-launch
+    // timing (profile), the per-generation moments kernel (it reads the whole state).
+    static const bool split_env = !(getenv("DEMCZ_LINREG_SPLIT") && atoi(getenv("DEMCZ_LINREG_SPLIT")) == 0);
+    const int nh = (split_env && CT >= 2 && !o.profile && !o.moments) ? 2 : 1;
+    const int CT0 = nh == 2 ? (CT + 1) / 2 : CT;
+    cudaStream_t st[2] = {c->stream, c->stream};
+    if (nh == 2) {
+        if (!s->hstream[0]) {
+            for (int h = 0; h < 2; ++h) {
+                CUL(c, cudaStreamCreateWithFlags(&s->hstream[h], cudaStreamNonBlocking));
+                CUL(c, cudaEventCreateWithFlags(&s->ev_join[h], cudaEventDisableTiming));
+            }
+            CUL(c, cudaEventCreateWithFlags(&s->ev_fork, cudaEventDisableTiming));
+        }
+        CUL(c, cudaEventRecord(s->ev_fork, c->stream));
+        for (int h = 0; h < 2; ++h) { st[h] = s->hstream[h]; CUL(c, cudaStreamWaitEvent(st[h], s->ev_fork, 0)); }
+    }
     for (int gi = 0; gi < n_gens; ++gi) {
         const int64_t grel = g + gi + 1;
         const int nb_run = snooker ? 1 : o.Nblocks;              // a snooker generation is ONE proposal moving all coordinates
         for (int b = 0; b < nb_run; ++b) {
-            LinArgs a;
-            memset(&a, 0, sizeof a);
-            a.X = c->dX; a.N = o.N; a.ldx = c->ldx; a.d = o.d; a.ppad = s->ppad;
-            a.chain_offset = (uint32_t)o.chain_offset;
-            a.Z = c->dZ; a.ZS = c->ZS;
-            a.Mdraw = Mdraw; a.zcap = (uint32_t)c->zcap; a.zstart = zstart;
-            a.gen = o.gen_offset + grel; a.grel = grel;
-            a.keys = c->keys;
-            a.block = b; a.nblocks = o.Nblocks;
-            uint64_t mask = 0;
-            for (int t = c->block_ptr[b]; t < c->block_ptr[b + 1]; ++t) mask |= (uint64_t)1 << c->block_idx[t];
-            a.mask_lo = (uint32_t)mask; a.mask_hi = (uint32_t)(mask >> 32);
-            const int blocklen = c->block_ptr[b + 1] - c->block_ptr[b];
-            a.cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
-            for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
-            a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
-            a.kind = s->kind; a.Dh = s->Dh; a.Dexp = s->Dexp; memcpy(a.xexp, s->xexp, sizeof a.xexp); a.swap_halves = s->swap_halves;
-            a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
-            a.flags = demcz_flags(c); a.world = o.world; a.my_rank = o.rank;
-            a.need = (gi == 0 && b == 0) ? demcz_comm_need(c) : 0ull;          // once per archive view
-            a.gamma_s = (float)o.snooker_gamma; a.geo = s->geo;
-            if (snooker && Mdraw < 3) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: the snooker update needs 3 drawable archive rows");
-            linreg_prepare_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(a, true, snooker);
-            CUL(c, cudaGetLastError());
+            for (int h = 0; h < nh; ++h) {
+                const int ct_lo = h == 0 ? 0 : CT0, ct_n = nh == 1 ? CT : (h == 0 ? CT0 : CT - CT0);
+                const int chain_lo = ct_lo * 128, chain_hi = std::min(o.N, (ct_lo + ct_n) * 128);
+                if (chain_lo >= chain_hi) continue;
+                const int n_sub = chain_hi - chain_lo;
+                LinArgs a;
+                memset(&a, 0, sizeof a);
+                a.X = c->dX; a.N = o.N; a.ldx = c->ldx; a.d = o.d; a.ppad = s->ppad;
+                a.chain_lo = chain_lo; a.chain_hi = chain_hi;
+                a.chain_offset = (uint32_t)o.chain_offset;
+                a.Z = c->dZ; a.ZS = c->ZS;
+                a.Mdraw = Mdraw; a.zcap = (uint32_t)c->zcap; a.zstart = zstart;
+                a.gen = o.gen_offset + grel; a.grel = grel;
+                a.keys = c->keys;
+                a.block = b; a.nblocks = o.Nblocks;
+                uint64_t mask = 0;
+                for (int t = c->block_ptr[b]; t < c->block_ptr[b + 1]; ++t) mask |= (uint64_t)1 << c->block_idx[t];
+                a.mask_lo = (uint32_t)mask; a.mask_hi = (uint32_t)(mask >> 32);
+                const int blocklen = c->block_ptr[b + 1] - c->block_ptr[b];
+                a.cscale = (float)(blocklen == 1 ? c->gamma : c->gamma / sqrt(2.0 * blocklen));   // src/demcz.jl:183-187
+                for (int k = 0; k < o.d; ++k) a.eps[k] = (float)c->eps[k];
+                a.Xprop = s->Xprop; a.wacc = s->wacc; a.Dhi = s->Dhi; a.Dlo = s->Dlo; a.lin = s->lin; a.b0 = s->d_b0; a.g = s->d_g;
+                a.kind = s->kind; a.Dh = s->Dh; a.Dexp = s->Dexp; memcpy(a.xexp, s->xexp, sizeof a.xexp); a.swap_halves = s->swap_halves;
+                a.tr_r1 = c->tr_r1; a.tr_r2 = c->tr_r2; a.tr_u = c->tr_u; a.tr_xprop = c->tr_xprop;
+                a.flags = demcz_flags(c); a.world = o.world; a.my_rank = o.rank;
+                a.need = (gi == 0 && b == 0) ? demcz_comm_need(c) : 0ull;          // once per archive view (and per half)
+                a.gamma_s = (float)o.snooker_gamma; a.geo = s->geo;
+                linreg_prepare_kernel<<<grid1(n_sub, 128), 128, 0, st[h]>>>(a, true, snooker);
+                CUL(c, cudaGetLastError());
 
-            if (o.profile) {
-                while (s->ev.size() < s->ev_used + 2) { cudaEvent_t ev; CUL(c, cudaEventCreate(&ev)); s->ev.push_back(ev); }
-                CUL(c, cudaEventRecord(s->ev[s->ev_used], c->stream));
+                if (o.profile) {
+                    while (s->ev.size() < s->ev_used + 2) { cudaEvent_t ev; CUL(c, cudaEventCreate(&ev)); s->ev.push_back(ev); }
+                    CUL(c, cudaEventRecord(s->ev[s->ev_used], st[h]));
+                }
+                // the GEMM of this half: operand rows, exponents and partial sums of chains [chain_lo, ...) through offset pointers
+                const size_t po = (size_t)chain_lo * s->ppad;
+                CUL(c, launch_ssr(c, s, s->Dhi ? s->Dhi + po : nullptr, s->Dlo ? s->Dlo + po : nullptr, ct_n, s->Npad, s->partial + chain_lo,
+                                  s->Dh ? s->Dh + po : nullptr, s->Dexp ? s->Dexp + chain_lo : nullptr, st[h]));
+                if (o.profile) { CUL(c, cudaEventRecord(s->ev[s->ev_used + 1], st[h])); s->ev_used += 2; }
+                if (h == 0) s->ssr_launches++;
+
+                AccArgs q;
+                memset(&q, 0, sizeof q);
+                q.X = c->dX; q.Xprop = s->Xprop; q.lp = s->lp64; q.wacc = s->wacc;
+                q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R * (kEpiWarps / 4);
+                q.chain_lo = chain_lo; q.chain_hi = chain_hi;
+                q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0; q.link = s->link;
+                q.tempered = o.anneal ? 1 : 0;
+                q.T = o.anneal ? c->hT[(size_t)grel - 1] : 1.f;
+                q.grel = grel; q.block = b; q.nblocks = o.Nblocks; q.last_block = (b == nb_run - 1);
+                q.geo = snooker ? s->geo : nullptr;
+                q.lp_gen0 = o.Nblocks > 1 ? s->lp64 + c->ldx : nullptr;
+                q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
+                q.count_run = (grel != 1) ? 1 : 0;
+                q.count_win = (o.anneal && o.adapt && (grel - 1) % o.adapt_every == 0) ? 0 : 1;
+                const bool keep = hist != nullptr && grel % c->thin == 0;           // history thinning (opts.thin)
+                q.hist = keep ? hist : nullptr; q.lphist = (double*)lphist; q.hidx = grel / c->thin - 1;
+                const bool do_append = append && gi == n_gens - 1;
+                q.Zw = do_append ? c->dZ : nullptr; q.ZS = c->ZS;
+                q.append_row0 = (uint32_t)(c->M % c->zcap); q.zcap = (uint32_t)c->zcap; q.chain_offset = (uint32_t)o.chain_offset;
+                if (acc) { q.S1 = c->dS1[half]; q.S2 = c->dS2 + (size_t)half * o.d; q.shift = c->dshift; }
+                q.tr_lpprop = c->tr_lpprop; q.tr_acc = c->tr_acc;
+                linreg_accept_kernel<<<grid1(n_sub, 128), 128, 0, st[h]>>>(q);
+                CUL(c, cudaGetLastError());
             }
-            CUL(c, launch_ssr(c, s, s->Dhi, s->Dlo, CT, s->Npad, s->partial));
-            if (o.profile) { CUL(c, cudaEventRecord(s->ev[s->ev_used + 1], c->stream)); s->ev_used += 2; }
-            s->ssr_launches++;
-
-            AccArgs q;
-            memset(&q, 0, sizeof q);
-            q.X = c->dX; q.Xprop = s->Xprop; q.lp = s->lp64; q.wacc = s->wacc;
-            q.N = o.N; q.ldx = c->ldx; q.d = o.d; q.Npad = s->Npad; q.R = s->R * (kEpiWarps / 4);
-            q.partial = s->partial; q.lin = s->lin; q.ssr0 = s->ssr0; q.link = s->link;
-            q.tempered = o.anneal ? 1 : 0;
-            q.T = o.anneal ? c->hT[(size_t)grel - 1] : 1.f;
-            q.grel = grel; q.block = b; q.nblocks = o.Nblocks; q.last_block = (b == nb_run - 1);
-            q.geo = snooker ? s->geo : nullptr;
-            q.lp_gen0 = o.Nblocks > 1 ? s->lp64 + c->ldx : nullptr;
-            q.chain_changed = c->d_chain_changed; q.win_changed = c->d_counters + 0; q.accepted_total = c->d_counters + 1;
-            q.count_run = (grel != 1) ? 1 : 0;
-            q.count_win = (o.anneal && o.adapt && (grel - 1) % o.adapt_every == 0) ? 0 : 1;
-            const bool keep = hist != nullptr && grel % c->thin == 0;           // history thinning (opts.thin)
-            q.hist = keep ? hist : nullptr; q.lphist = (double*)lphist; q.hidx = grel / c->thin - 1;
-            const bool do_append = append && gi == n_gens - 1;
-            q.Zw = do_append ? c->dZ : nullptr; q.ZS = c->ZS;
-            q.append_row0 = (uint32_t)(c->M % c->zcap); q.zcap = (uint32_t)c->zcap; q.chain_offset = (uint32_t)o.chain_offset;
-            if (acc) { q.S1 = c->dS1[half]; q.S2 = c->dS2 + (size_t)half * o.d; q.shift = c->dshift; }
-            q.tr_lpprop = c->tr_lpprop; q.tr_acc = c->tr_acc;
-            linreg_accept_kernel<<<grid1(o.N, 128), 128, 0, c->stream>>>(q);
-            CUL(c, cudaGetLastError());
         }
         if (o.moments) { int rc = demcz_moments_add_state(c); if (rc != DEMCZ_OK) return rc; }
     }
+    if (nh == 2)
+        for (int h = 0; h < 2; ++h) { CUL(c, cudaEventRecord(s->ev_join[h], st[h])); CUL(c, cudaStreamWaitEvent(c->stream, s->ev_join[h], 0)); }
     return demcz_hist_end(c, g, n_gens);
 }
