@@ -411,6 +411,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-probe", action="store_true")
+    ap.add_argument("--moments", action="store_true", help="opts.moments on (streaming mean / covariance of every generation inside the step kernel): what it costs")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         print(f"note: --warmup {args.warmup} < 3 breaks the timing rules; use for profiling only", file=sys.stderr)
@@ -508,7 +509,7 @@ def main():
 
     def sampler_kwargs(w):
         return dict(K=w["K"], blockindex=w["blocks"], eps_scale=1e-5 * np.ones(w["d"]), γ=w["gamma"], anneal=w["anneal"], T0=2.0, TN=1e-4,
-                    adapt=False)
+                    adapt=False, moments=args.moments)
 
     # ---- parity probe of one workload at its benchmark size (this rank's GPU; a world=1 context) ----------------
     def parity_probe(w, s_timed, Z0):

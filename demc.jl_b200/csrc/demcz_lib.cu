@@ -556,7 +556,9 @@ extern "C" int demcz_create(demcz_ctx** out, const demcz_opts* o, int device)
     }
     c->thin = o->thin > 1 ? o->thin : 1;
     // small-N persistent launches: every chain in one CTA of the step kernel, one GPU, padded slots, no streaming moments
-    c->persistent_ok = o->persistent != 0 && o->world == 1 && o->N <= 128 && !o->moments && o->d <= DEMCZ_MAX_DIM && c->ZS == zslot(c->LD);
+    // (the streamed history's slice buffers hold one K-block: store_chain = 2 keeps one launch per K-block)
+    c->persistent_ok = o->persistent != 0 && o->world == 1 && o->N <= 128 && !o->moments && o->store_chain != 2 && o->d <= DEMCZ_MAX_DIM &&
+                       c->ZS == zslot(c->LD);
     if (o->store_chain == 1 && o->Ngeneration / c->thin > 0) {
         alloc((void**)&c->dhist, (size_t)(o->Ngeneration / c->thin) * o->d * o->N * sizeof(float));
         alloc((void**)&c->dlphist, (size_t)(o->Ngeneration / c->thin) * o->N * sizeof(float));
