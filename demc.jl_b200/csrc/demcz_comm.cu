@@ -317,8 +317,10 @@ extern "C" int demcz_comm_open_peers(demcz_ctx* c, const uint8_t* infos)
                 cudaStreamSynchronize(c->comm_stream) != cudaSuccess) { cudaGetLastError(); c->memop_wait = false; }
         }
     }
-    // every rank takes the same decision (same opts, same driver).  AUTO: copy engines (measured)
-    c->push_engine = c->o.push_engine == DEMCZ_PUSH_KERNEL ? 0 : 1;
+    // every rank takes the same decision (same opts, same driver).  AUTO (measured): copy engines up to
+    // 4 GPUs (26.2 vs 18.0 G chain-updates/s on 2, 42.7 on 4), the push kernel above (8 GPUs: 7 peer copies per K-block move
+    // only ~290 GB/s next to the step kernel; SM-issued stores started together with the step kernel reach 545 GB/s)
+    c->push_engine = c->o.push_engine == DEMCZ_PUSH_KERNEL ? 0 : c->o.push_engine == DEMCZ_PUSH_COPY_ENGINE ? 1 : (c->o.world <= 4 ? 1 : 0);
     if (const char* env = getenv("DEMCZ_PUSH_ENGINE")) c->push_engine = (atoi(env) == DEMCZ_PUSH_COPY_ENGINE) ? 1 : 0;
     c->inkernel_poll = c->push_engine == 1 && c->memop_write;
     if (!c->inkernel_poll) c->memop_wait = false;                  // the wait kernel path keeps the event hand-off
