@@ -36,10 +36,11 @@ cudaError_t launch_step_t(demcz_ctx* c, const StepArgs& a)
     const MvnParams<LD> P = demcz_make_mvn_params<LD>(c, kStepOpt & OPT_JMAJOR);
     // Programmatic dependent launch: consecutive step launches of a stream overlap the next launch's scheduling and
     // prologue with this one's tail; the kernel waits (griddepcontrol.wait) before it touches anything a predecessor wrote.
-    // One GPU only: on a sharded run the launch attribute costs the overlap of the exchange with the step kernel
-    // (8 GPUs, C4: 49.9 G chain-updates/s with it, 70.6 G without; profiles/r2_c4_8gpu_pdl_*.json).  DEMCZ_PDL=0/1 forces it.
+    // Not on the push-kernel transport: there the launch attribute costs the overlap of the push with the step kernel
+    // (8 GPUs, C4: 49.9 G chain-updates/s with it, 70.6 G without; profiles/r2_c4_8gpu_pdl_*.json); with the copy engines
+    // it is worth +2 % on 2 GPUs and nothing on 4.  DEMCZ_PDL=0/1 forces it.
     static const int pdl_env = getenv("DEMCZ_PDL") ? atoi(getenv("DEMCZ_PDL")) : -1;
-    const bool pdl = pdl_env >= 0 ? pdl_env != 0 : c->o.world == 1;
+    const bool pdl = pdl_env >= 0 ? pdl_env != 0 : (c->o.world == 1 || c->inkernel_poll);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(threads); cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
