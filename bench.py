@@ -708,6 +708,8 @@ def main():
             roof = dict(bound="tensor", kernel=kinfo.get("linreg_kernel", "linreg_ssr_kernel (tcgen05 kind::tf32, 3xTF32)"),
                         achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
                         peak_source=f"{bf16_src} = {bf16:.0f} TFLOP/s dense bf16; kind::{kind} dense rate = {dense:.0f}; / {terms} MMA terms per FP32-equivalent product",
+                        frac_vs_sustained=(achieved / ((float(peaks["bf16_tflops_sustained"]) if kind == "f16" else float(peaks["bf16_tflops_sustained"]) / 2.0) / terms))
+                        if "bf16_tflops_sustained" in peaks else None,
                         frac_vs_live_tf32=(achieved / (tf32_live / 3.0)) if kind == "tf32" else None,
                         tf32_dense_live_tflops=tf32_live,
                         tensor_issued_tflops=terms * achieved, launch_us=avg_ms * 1e3,
