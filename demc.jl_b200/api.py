@@ -460,6 +460,8 @@ def _run(logobj, Zmat, v, *, anneal, prevrun, verbose, print_step, autostop, aut
             X, lp = _dist.allgather_rows(X, local_rank), _dist.allgather_rows(lp, local_rank)
             chain, log_obj = _dist.allgather_rows(chain, local_rank), _dist.allgather_rows(log_obj, local_rank)
     finally:
+        if world > 1:
+            _dist.barrier()                               # no rank frees its archive while a peer still has it mapped
         s.close()
     mc = MC(np.asfortranarray(chain), np.asfortranarray(log_obj), X, lp, s.generations_total, info)
     return _concat_prev(prevrun, mc), Z

@@ -15,7 +15,7 @@ from typing import Optional, Tuple
 import numpy as np
 
 __all__ = ["shard", "env_rank_world", "broadcast_unique_id", "make_sharded_sampler", "open_peer_archives",
-           "ensure_process_group", "pad_archive_for_sharding", "allgather_rows", "allreduce_sum"]
+           "ensure_process_group", "pad_archive_for_sharding", "allgather_rows", "allreduce_sum", "barrier"]
 
 
 def shard(N_global: int, rank: int, world: int) -> Tuple[int, int]:
@@ -141,3 +141,9 @@ def allreduce_sum(x, local_rank=0):
     t = torch.tensor([float(x)], dtype=torch.float64, device=_dev(local_rank))
     dist.all_reduce(t)
     return float(t.item())
+
+
+def barrier():
+    import torch.distributed as dist
+    if dist.is_initialized():
+        dist.barrier()

@@ -508,3 +508,19 @@ def test_persistent_path_stepwise_against_oracle():
     st = check_run_against_oracle(DEMC.MvNormalLogpdf(mu, S), _z0(10 * d + N, d), N=N, K=10, G=60, blocks=[list(range(d))],
                                   eps=1e-5 * np.ones(d), gamma=2.38, seed=31953150)
     assert st["accepted"] > 0
+
+
+def test_anneal_par_entry_point_adapts_gamma_per_sync_block():
+    # demcz_anneal_par (src/demcz_anneal.jl:82-140): γ is adapted once per sync block from the block's accept ratio
+    # (:123-132 — the rule of :48-57 with adapt_every = sync_every); positional default TN = 1e-3 (:86)
+    d, N, every, G = 4, 64, 15, 60
+    mu = np.linspace(-1, 1, d)
+    mc, Z = DEMC.demcz_anneal_par(DEMC.QuadraticLogobj(mu), _z0(3 * N, d), N, 5, G, 1, [list(range(d))], 1e-5 * np.ones(d), 2.38,
+                                  sync_every=every, T0=2.0, verbose=False)
+    assert mc.chain.shape == (N, d, G) and Z.shape[0] == 3 * N + N * (G // 5)
+    gamma = 2.38
+    for w in range(G // every):
+        win = mc.log_obj[:, w * every:(w + 1) * every]
+        ar = np.count_nonzero(np.diff(win, axis=1) != 0) / (N * every)
+        gamma = max(0.1, gamma / 2) if ar < 0.1 else (min(4.0, 1.5 * gamma) if ar > 0.5 else gamma)
+    assert mc.info["final_gamma"] == gamma
