@@ -90,3 +90,44 @@ def test_world2_sharded_protocol_matches_single_rank(coracle):
     same_X, same_Z, M, Mref = q.get()
     assert M == Mref
     assert same_X and same_Z
+
+
+def _helpers_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    try:
+        ddist.ensure_process_group(rank)                     # gloo here (no CUDA): the torchrun environment is enough
+        assert dist.is_initialized() and dist.get_world_size() == world
+        a = np.asfortranarray(np.arange(12, dtype=np.float64).reshape(3, 2, 2) + 100 * rank)
+        g = ddist.allgather_rows(a, rank)                    # rank order = global chain order
+        assert g.shape == (3 * world, 2, 2) and np.array_equal(g[:3], a - 100 * rank) and np.array_equal(g[3:6], a - 100 * rank + 100)
+        assert ddist.allreduce_sum(rank + 1.0, rank) == sum(range(1, world + 1))
+        ddist.barrier()
+        q.put((rank, "ok"))
+    except Exception as e:  # noqa: BLE001
+        q.put((rank, repr(e)))
+    finally:
+        if dist.is_initialized():
+            dist.destroy_process_group()
+
+
+def test_sharded_entry_point_helpers_gloo():
+    """Host plumbing of the _par entry points (api._run, sharded): process group from the torchrun environment, rank-ordered
+    all-gather of the per-rank results, reductions — on CPU with gloo, world size 2."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    ps = [ctx.Process(target=_helpers_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in ps:
+        p.start()
+    res = dict(q.get(timeout=120) for _ in range(world))
+    for p in ps:
+        p.join(60)
+    assert res == {0: "ok", 1: "ok"}, res
+
+
+def test_pad_archive_for_sharding():
+    Z = np.arange(14, dtype=np.float64).reshape(7, 2)
+    Zp, cap = ddist.pad_archive_for_sharding(Z, 4, 25, 10)          # 7 rows -> 8 (one oldest row repeated in front), 3 appends of 4
+    assert Zp.shape == (8, 2) and np.array_equal(Zp[1:], Z) and np.array_equal(Zp[0], Z[0]) and cap == 8 + 4 * 3
+    Zq, cap = ddist.pad_archive_for_sharding(Z[:4], 4, 20, 10)
+    assert Zq.shape == (4, 2) and cap == 4 + 8

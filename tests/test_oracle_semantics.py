@@ -40,3 +40,53 @@ def test_inloop_and_gen_sync_append_sample_the_same_posterior(coracle):
     mb, Cb = orc.mean_cov_chain(b["chain"][:, :, G // 2:])
     assert np.all(np.abs(ma - mb) < 0.1 * sd)
     assert np.linalg.norm(Ca - Cb) / np.linalg.norm(S) < 0.15
+
+
+def test_snooker_update_draws_distinct_rows_and_keeps_the_target_invariant():
+    """Restatement of the snooker update of ter Braak & Vrugt (2008) (cited at README.md:57-59 upstream, no reference code):
+    z, z1, z2 are distinct; with the (d-1) log|x'-z|/|x-z| Jacobian term the update leaves N(0, I) invariant."""
+    import numpy as np
+    from oracle import demcz_oracle as orc
+    rng = np.random.default_rng(0)
+    d, M, N = 3, 1500, 400
+    lik = orc.MvNormalLik(np.zeros(d), np.eye(d))
+    Z = rng.normal(size=(M, d))
+    X = rng.normal(size=(N, d))
+    lp = lik.logdensity(X)
+    xs, acc = [], 0.0
+    for g in range(1, 301):
+        o = orc.snooker_update(X, lp, Z, M, lik, 0.0, 11, g)
+        assert np.all(o["z"] != o["r1"]) and np.all(o["z"] != o["r2"]) and np.all(o["r1"] != o["r2"])
+        assert o["r1"].max() < M and o["r2"].max() < M and o["z"].max() < M
+        a = o["accepted"]
+        X[a], lp[a] = o["xprop"][a], o["lp_prop"][a]
+        acc += a.mean()
+        if g > 100:
+            xs.append(X.copy())
+    xs = np.concatenate(xs)
+    assert 0.2 < acc / 300 < 0.7
+    assert np.all(np.abs(xs.mean(0)) < 0.05) and np.all(np.abs(xs.var(0) - 1.0) < 0.05)
+    # exhaustive check of the index mapping on a tiny archive: the ordered triple is uniform over distinct triples
+    cnt = {}
+    for g in range(1, 400):
+        o = orc.snooker_update(X[:200], lp[:200], Z, 4, lik, 1.7, 5, g)
+        for t in zip(o["z"], o["r1"], o["r2"]):
+            cnt[t] = cnt.get(t, 0) + 1
+    assert len(cnt) == 24 and min(cnt.values()) > 0.8 * 399 * 200 / 24 and max(cnt.values()) < 1.2 * 399 * 200 / 24
+
+
+def test_snooker_generation_choice_has_the_asked_frequency():
+    from oracle import demcz_oracle as orc
+    hits = sum(orc.is_snooker_gen(31953150, g, 0.1) for g in range(1, 20001))
+    assert 1800 < hits < 2200
+    assert not any(orc.is_snooker_gen(1, g, 0.0) for g in range(1, 100))
+
+
+def test_logistic_lik_matches_a_direct_evaluation():
+    import numpy as np
+    from oracle import demcz_oracle as orc
+    rng = np.random.default_rng(1)
+    X = rng.normal(size=(50, 3)); y = (rng.random(50) < 0.5).astype(float)
+    B = rng.normal(size=(4, 3))
+    want = [np.sum(y * (X @ b) - np.log1p(np.exp(X @ b))) for b in B]
+    np.testing.assert_allclose(orc.LogisticLik(X, y).logdensity(B), want, rtol=1e-12)
