@@ -1112,11 +1112,9 @@ extern "C" int demcz_run(demcz_ctx* c, int64_t max_generations, demcz_run_info* 
                 a.done_seq = (unsigned int)(c->appends + 1);
                 c->last_append_by_step_kernel = true;
             }
-            static const bool step_events = getenv("DEMCZ_STEP_EVENTS") && atoi(getenv("DEMCZ_STEP_EVENTS")) == 1;     // experiment switch
-            const size_t evi = o.profile ? n_launch : n_launch % 64;
-            if (o.profile || step_events) CU(c, cudaEventRecord(pool_event(c, 2 * evi), c->stream));
+            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch), c->stream));
             CU(c, demcz_launch_step(c, a, acc, full));
-            if (o.profile || step_events) CU(c, cudaEventRecord(pool_event(c, 2 * evi + 1), c->stream));
+            if (o.profile) CU(c, cudaEventRecord(pool_event(c, 2 * n_launch + 1), c->stream));
             ++n_launch;
             rc = demcz_hist_end(c, g, n_gens);
             if (rc != DEMCZ_OK) return rc;
