@@ -158,10 +158,12 @@ function demcz_sample(logobj, Zmat, opts::DEMCopt; prevrun=nothing)
                  autostop_Rhat=opts.autostop_Rhat, autostop_every=opts.autostop_every)
 end
 
+# `ext...`: the keyword extensions of run_gpu with no counterpart in the reference (thin, moments, snooker_prob, snooker_gamma,
+# seed, device, store_chain), all off by default
 function demcz_sample(logobj, Zmat, N=4, K=10, Ngeneration=5000, Nblocks=1, blockindex=[1:size(Zmat, 2)], eps_scale=1e-4 * ones(size(Zmat, 2)), γ=2.38;
-                      prevrun=nothing, verbose=true, print_step=100, autostop=:no, autostop_Rhat=1.01, autostop_every=1000)
+                      prevrun=nothing, verbose=true, print_step=100, autostop=:no, autostop_Rhat=1.01, autostop_every=1000, ext...)
     run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale, γ; anneal=false, prevrun=prevrun, autostop=autostop,
-            autostop_Rhat=autostop_Rhat, autostop_every=autostop_every, T0=3.0, TN=1e-3, temperaturefun=tempbaseline, adaptγ=Dict())
+            autostop_Rhat=autostop_Rhat, autostop_every=autostop_every, T0=3.0, TN=1e-3, temperaturefun=tempbaseline, adaptγ=Dict(), ext...)
 end
 
 function demcz_anneal(logobj, Zmat, opts::DEMCopt; prevrun=nothing, temperaturefun=tempbaseline,
@@ -173,13 +175,15 @@ end
 
 function demcz_anneal(logobj, Zmat, N=4, K=10, Ngeneration=5000, Nblocks=1, blockindex=[1:size(Zmat, 2)], eps_scale=1e-4 * ones(size(Zmat, 2)), γ=2.38;
                       prevrun=nothing, verbose=true, print_step=100, T0=3, TN=0,
-                      temperaturefun=tempbaseline, adaptγ=Dict("adapt" => true, "minγ" => 0.1, "maxγ" => 4.0, "adapt_every" => 500))
+                      temperaturefun=tempbaseline, adaptγ=Dict("adapt" => true, "minγ" => 0.1, "maxγ" => 4.0, "adapt_every" => 500), ext...)
     run_gpu(logobj, Zmat, N, K, Ngeneration, Nblocks, blockindex, eps_scale, γ; anneal=true, prevrun=prevrun, autostop=:no,
-            autostop_Rhat=1.01, autostop_every=1000, T0=Float64(T0), TN=Float64(TN), temperaturefun=temperaturefun, adaptγ=adaptγ)
+            autostop_Rhat=1.01, autostop_every=1000, T0=Float64(T0), TN=Float64(TN), temperaturefun=temperaturefun, adaptγ=adaptγ, ext...)
 end
 
 # ---- the parallel entry points (src/demcz.jl:101-165, src/demcz_anneal.jl:82-140): every chain is a GPU thread, the
-# sync block is the R-hat / γ-adaptation window; `workerpool` is accepted and ignored ------------------------------
+# sync block is the R-hat / γ-adaptation window; `workerpool` is accepted and ignored.  This shim drives ONE GPU; the
+# multi-GPU runner (one process per GPU, demcz_comm_* of include/demcz.h) is wired in the Python host
+# (demc.jl_b200/api.py::_run with sharded=true, dist.py) and needs a per-GPU process launcher on the Julia side ------
 function demcz_sample_par(logobj, Zmat, opts::DEMCopt; sync_every=1000, prevrun=nothing, workerpool=nothing)
     demcz_sample(logobj, Zmat, opts.N, opts.K, opts.Ngeneration, opts.Nblocks, opts.blockindex, opts.eps_scale, opts.γ;
                  prevrun=prevrun, verbose=opts.verbose, autostop=opts.autostop, autostop_Rhat=opts.autostop_Rhat, autostop_every=sync_every)
