@@ -233,3 +233,74 @@ def test_par_entry_points_under_torchrun(tmp_path):
     np.testing.assert_allclose(a["rhat"], b["rhat"], rtol=1e-6)
     assert int(a["accepted"]) == int(b["accepted"]) and int(a["a_accepted"]) == int(b["a_accepted"])
     assert float(a["a_gamma"]) == float(b["a_gamma"])
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("kind,sync_mode", [("mvn", "overlap"), ("mvn", "strict"), ("logistic", "overlap")])
+def test_two_gpus_snooker_and_logistic_bitwise(kind, sync_mode):
+    """The round-2 extensions on a sharded run: snooker generations (own kernel, polls the segment flags itself), R-hat
+    accumulators and history moments across ranks, the logistic likelihood — bit-identical to one GPU."""
+    rng = np.random.default_rng(4)
+    N, K, G = 512, 4, 32
+    if kind == "mvn":
+        d = 9
+        S = 0.4 * np.ones((d, d)) + 0.6 * np.eye(d)
+        mu = np.linspace(-1, 1, d)
+        make = lambda: DEMC.MvNormalLogpdf(mu, S)
+        Z0 = rng.normal(size=(2 * N, d))
+    else:
+        n, d = 3000, 7
+        X = np.ones((n, d)); X[:, 1:] = rng.normal(size=(n, d - 1))
+        beta = rng.normal(size=d) / 3
+        y = (rng.random(n) < 1 / (1 + np.exp(-X @ beta))).astype(float)
+        make = lambda: DEMC.LogisticLoglik(X, y)
+        Z0 = beta + 0.2 * rng.normal(size=(2 * N, d))
+    kw = dict(K=K, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d), γ=2.2, seed=21, store_chain=False,
+              sync_mode=sync_mode, snooker_prob=0.3, autostop=True, autostop_every=16, autostop_Rhat=0.0, moments=(kind == "mvn"))
+    with DEMC.Sampler(make(), d, N=N, device=0, **kw) as s:
+        s.set_archive(Z0)
+        info1 = s.run()
+        (X1, lp1), Z1, rhat1 = s.get_state(), s.get_archive(), s.get_rhat()
+        mom1 = s.get_history_moments() if kind == "mvn" else None
+    lib = _lib.load()
+    buf = (C.c_uint8 * 128)()
+    assert lib.demcz_comm_unique_id(buf) == 0
+    uid, world = bytes(buf), 2
+    out, infos, err = [None] * world, [None] * world, []
+    bar = threading.Barrier(world)
+
+    def work(r):
+        try:
+            n_loc, off = ddist.shard(N, r, world)
+            s = DEMC.Sampler(make(), d, N=n_loc, rank=r, world=world, N_global=N, chain_offset=off, device=r, **kw)
+            s.set_archive(Z0)
+            s.comm_init(uid)
+            infos[r] = s.peer_info()
+            bar.wait(60)
+            s.open_peers(b"".join(infos))
+            bar.wait(60)
+            info = s.run()
+            mom = s.get_history_moments() if kind == "mvn" else None        # collective (all-reduce): every rank calls it
+            out[r] = (s.get_state(), s.get_archive(), info, s.get_rhat(), mom)
+            bar.wait(60)
+            s.close()
+        except Exception as e:  # noqa: BLE001
+            err.append(e)
+            bar.abort()
+
+    th = [threading.Thread(target=work, args=(r,)) for r in range(world)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(300)
+    assert not err, err
+    np.testing.assert_array_equal(np.concatenate([o[0][0] for o in out]), X1)
+    np.testing.assert_array_equal(np.concatenate([o[0][1] for o in out]), lp1)
+    for o in out:
+        np.testing.assert_array_equal(o[1], Z1)
+        np.testing.assert_allclose(o[3], rhat1, rtol=1e-6)
+        if mom1 is not None:
+            assert o[4][2] == mom1[2]
+            np.testing.assert_allclose(o[4][0], mom1[0], rtol=1e-9, atol=1e-12)
+            np.testing.assert_allclose(o[4][1], mom1[1], rtol=1e-6, atol=1e-12)
+    assert sum(o[2]["accepted"] for o in out) == info1["accepted"]

@@ -524,3 +524,25 @@ def test_anneal_par_entry_point_adapts_gamma_per_sync_block():
         ar = np.count_nonzero(np.diff(win, axis=1) != 0) / (N * every)
         gamma = max(0.1, gamma / 2) if ar < 0.1 else (min(4.0, 1.5 * gamma) if ar > 0.5 else gamma)
     assert mc.info["final_gamma"] == gamma
+
+
+def test_rhat_and_moments_with_snooker_generations_match_the_stored_history():
+    # the snooker kernel feeds the same streaming accumulators (split-Rhat sums, history moments, accept counts) as the fused
+    # step kernel: Rhat_gelman (src/utils.jl:2-20) and mean_cov_chain (:96-106) on the stored chain must agree
+    d, N, every, G = 6, 300, 40, 80
+    mu, S = example_normpdf_target(d)
+    with DEMC.Sampler(DEMC.MvNormalLogpdf(mu, S), d, N=N, K=5, Ngeneration=G, blockindex=[list(range(d))], eps_scale=1e-5 * np.ones(d),
+                      γ=2.38, seed=12, store_chain=True, autostop=True, autostop_every=every, autostop_Rhat=0.0, moments=True,
+                      snooker_prob=0.25) as s:
+        s.set_archive(_z0(2 * N, d, scale=0.3))
+        s.run()
+        chain, log_obj = s.get_chain()
+        rhat = s.get_rhat()
+        m, c, n = s.get_history_moments()
+        counts = s.get_accept_counts()
+    np.testing.assert_allclose(rhat, orc.rhat_gelman(chain[:, :, every:]), rtol=5e-4)
+    mref, cref = DEMC.mean_cov_chain(chain)
+    assert n == N * G
+    np.testing.assert_allclose(m, mref, rtol=1e-6, atol=1e-9)
+    np.testing.assert_allclose(c, cref, rtol=2e-5, atol=1e-9 * np.abs(cref).max())
+    np.testing.assert_array_equal(counts, np.sum(np.diff(log_obj, axis=1) != 0.0, axis=1))
