@@ -301,6 +301,7 @@ def test_two_gpus_snooker_and_logistic_bitwise(kind, sync_mode):
         np.testing.assert_allclose(o[3], rhat1, rtol=1e-6)
         if mom1 is not None:
             assert o[4][2] == mom1[2]
-            np.testing.assert_allclose(o[4][0], mom1[0], rtol=1e-9, atol=1e-12)
-            np.testing.assert_allclose(o[4][1], mom1[1], rtol=1e-6, atol=1e-12)
+            # FP32 partial sums per warp, FP32 shared-memory atomics per CTA (order varies), FP64 across CTAs and ranks
+            np.testing.assert_allclose(o[4][0], mom1[0], rtol=1e-6, atol=1e-9)
+            np.testing.assert_allclose(o[4][1], mom1[1], rtol=1e-5, atol=1e-9)
     assert sum(o[2]["accepted"] for o in out) == info1["accepted"]
