@@ -50,7 +50,7 @@ EXPORTS = [
     "demcz_version", "demcz_create", "demcz_destroy", "demcz_last_error", "demcz_set_likelihood_mvnormal",
     "demcz_set_likelihood_linreg", "demcz_set_likelihood_logistic", "demcz_set_archive", "demcz_set_state", "demcz_set_temperature_table",
     "demcz_run", "demcz_get_kernel_info", "demcz_set_profile", "demcz_get_chain", "demcz_get_state", "demcz_get_archive", "demcz_get_moments", "demcz_get_archive_moments",
-    "demcz_get_history_moments", "demcz_get_archive_checksum", "demcz_get_rhat",
+    "demcz_get_history_moments", "demcz_get_archive_checksum", "demcz_archive_view_rule", "demcz_get_rhat",
     "demcz_get_accept_counts", "demcz_eval_logdensity", "demcz_get_trace", "demcz_comm_unique_id", "demcz_comm_init", "demcz_comm_peer_info", "demcz_comm_open_peers",
 ]
 
@@ -89,6 +89,7 @@ def load():
     lib.demcz_get_archive_moments.argtypes = [vp, i64, i64, dp, dp]
     lib.demcz_get_history_moments.argtypes = [vp, dp, dp, C.POINTER(i64), C.c_int32]
     lib.demcz_get_archive_checksum.argtypes = [vp, i64, i64, C.POINTER(C.c_uint64)]
+    lib.demcz_archive_view_rule.argtypes = [i64, i64, i64, C.c_int32, i64, i64, C.POINTER(i64), C.POINTER(i64)]
     lib.demcz_get_rhat.argtypes = [vp, dp]
     lib.demcz_get_accept_counts.argtypes = [vp, C.POINTER(i64)]
     lib.demcz_eval_logdensity.argtypes = [vp, dp, i64, dp]

@@ -769,26 +769,38 @@ static int init_state_if_needed(demcz_ctx* c)
 //    Applied for every world size, so a wrapped run is still independent of the sharding and bit-reproducible.
 // NCCL transport: also makes the compute stream wait (event) until the newest drawable segment has been gathered; the
 // peer-push transport needs no stream operation — the gathering kernels poll the flag words (demcz_comm_need).
+// The rule itself, free of any device state (exported for the CPU model check of the exchange protocol,
+// tests/test_exchange_protocol_model.py): rows appended so far M, ring capacity, rows per segment, sync mode, segments
+// appended so far on this archive, appends this context will still make -> (drawable rows, physical row of logical row 0).
+extern "C" int demcz_archive_view_rule(int64_t M, int64_t zcap, int64_t N_global, int32_t overlap, int64_t appends, int64_t remaining,
+                                       int64_t* m_out, int64_t* z0_out)
+{
+    const int64_t pend = (overlap && appends > 0) ? N_global : 0;
+    const int64_t ahead = std::max<int64_t>(0, std::min<int64_t>(overlap ? 2 : 1, remaining));
+    const int64_t T = M + ahead * N_global;                   // rows [M, T) may be written while this K-block draws
+    int64_t m, z0;
+    if (T > zcap) {                                           // they land on the oldest rows: keep off them
+        z0 = (T - zcap) % zcap;
+        m = zcap - ahead * N_global - pend;
+    } else if (M > zcap) {                                    // wrapped ring, no further append
+        z0 = M % zcap;
+        m = zcap - pend;
+    } else {
+        z0 = 0;
+        m = M - pend;
+    }
+    *m_out = m;
+    *z0_out = z0;
+    return m >= 2 ? DEMCZ_OK : DEMCZ_ERR_INVALID;
+}
+
 int demcz_archive_view(demcz_ctx* c, uint32_t* Mdraw, uint32_t* zstart)
 {
     const demcz_opts& o = c->o;
     const bool overlap = o.sync_mode == DEMCZ_SYNC_OVERLAP;
-    const int64_t pend = (overlap && c->appends > 0) ? o.N_global : 0;
-    const int64_t remaining = (int64_t)o.Ngeneration / o.K - c->appends_run;       // appends this context will still make
-    const int64_t ahead = std::max<int64_t>(0, std::min<int64_t>(overlap ? 2 : 1, remaining));
-    const int64_t T = c->M + ahead * o.N_global;              // rows [M, T) may be written while this K-block draws
     int64_t m, z0;
-    if (T > c->zcap) {                                        // they land on the oldest rows: keep off them
-        z0 = (T - c->zcap) % c->zcap;
-        m = c->zcap - ahead * o.N_global - pend;
-    } else if (c->M > c->zcap) {                              // wrapped ring, no further append
-        z0 = c->M % c->zcap;
-        m = c->zcap - pend;
-    } else {
-        z0 = 0;
-        m = c->M - pend;
-    }
-    if (m < 2) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: fewer than 2 drawable archive rows (M=%lld, capacity=%lld)", (long long)c->M, (long long)c->zcap);
+    const int ok = demcz_archive_view_rule(c->M, c->zcap, o.N_global, overlap ? 1 : 0, c->appends, (int64_t)o.Ngeneration / o.K - c->appends_run, &m, &z0);
+    if (ok != DEMCZ_OK) return demcz_fail(c, DEMCZ_ERR_INVALID, "demcz_run: fewer than 2 drawable archive rows (M=%lld, capacity=%lld)", (long long)c->M, (long long)c->zcap);
     *Mdraw = (uint32_t)m;
     *zstart = (uint32_t)z0;
     if (o.world > 1 && !c->peers_open && overlap && c->appends >= 2 && c->vis_waited < c->appends - 1) {

@@ -192,6 +192,13 @@ int demcz_get_history_moments(demcz_ctx* ctx, double* mean, double* cov, int64_t
  * the FP32 rows mixed with their logical position): equal on every rank of a sharded run iff the replicas are identical.
  * No reference counterpart (the reference shares one Z through a SharedArray, src/demcz.jl:109). */
 int demcz_get_archive_checksum(demcz_ctx* ctx, int64_t first_row, int64_t n_rows, uint64_t* checksum);
+/* The drawable view of the archive ring as a pure function (no context, no device): which rows a K-block may draw from
+ * so that neither this rank's next append nor — in overlap mode — a peer's push of the segment after it can touch them.
+ * M rows appended so far, ring capacity zcap, N_global rows per segment, overlap = DEMCZ_SYNC_OVERLAP, `appends` segments
+ * appended so far on this archive, `remaining` appends the run will still make.  Outputs: number of drawable rows and the
+ * physical row of logical row 0.  Exported for the CPU model check of the exchange protocol (tests/). */
+int demcz_archive_view_rule(int64_t M, int64_t zcap, int64_t N_global, int32_t overlap, int64_t appends, int64_t remaining,
+                            int64_t* m_out, int64_t* z0_out);
 /* last split-Rhat vector (Rhat_gelman, src/utils.jl:2-20), d values */
 int demcz_get_rhat(demcz_ctx* ctx, double* rhat);
 /* per-chain count of generations (2..G of this context) whose log-objective changed:
