@@ -775,6 +775,7 @@ static int init_state_if_needed(demcz_ctx* c)
 extern "C" int demcz_archive_view_rule(int64_t M, int64_t zcap, int64_t N_global, int32_t overlap, int64_t appends, int64_t remaining,
                                        int64_t* m_out, int64_t* z0_out)
 {
+    if (!m_out || !z0_out || zcap <= 0 || N_global <= 0 || M < 0) return DEMCZ_ERR_INVALID;
     const int64_t pend = (overlap && appends > 0) ? N_global : 0;
     const int64_t ahead = std::max<int64_t>(0, std::min<int64_t>(overlap ? 2 : 1, remaining));
     const int64_t T = M + ahead * N_global;                   // rows [M, T) may be written while this K-block draws
