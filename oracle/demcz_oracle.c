@@ -106,6 +106,20 @@ double orc_logdensity(const orc_lik* lik, const double* x)
         }
         if (y != ybuf) free(y);
         return lik->c0 - 0.5 * q;
+    } else if (lik->kind == ORC_LIK_LOGISTIC) {
+        /* Bernoulli-logit GLM, sum(y*eta - log(1 + exp(eta))), eta = X b: an extension (the reference takes any closure,
+         * src/demcz.jl:189); textbook formula with the overflow-safe softplus max(eta,0) + log1p(exp(-|eta|)) */
+        const int64_t n = lik->n;
+        double* eta = (double*)calloc((size_t)n, sizeof(double));
+        for (int k = 0; k < d; ++k) {
+            const double bk = x[k];
+            const double* col = lik->X + (size_t)n * k;
+            for (int64_t i = 0; i < n; ++i) eta[i] += col[i] * bk;
+        }
+        double s = 0.0;
+        for (int64_t i = 0; i < n; ++i) s += lik->y[i] * eta[i] - (fmax(eta[i], 0.0) + log1p(exp(-fabs(eta[i]))));
+        free(eta);
+        return s;
     } else {
         const int64_t n = lik->n;
         double* r = (double*)malloc(sizeof(double) * (size_t)n);   /* y .- X*b temporary */
@@ -339,4 +353,75 @@ int orc_run(const orc_opts* o, const orc_run_opts* r, const orc_lik* lik,
     free(lp_prev);
     if (info) { info->generations_done = done; info->stopped_by_rhat = stopped; info->final_gamma = oo.gamma; info->M = M; }
     return 0;
+}
+
+
+/* ---------------------------------------------------------------------------------------------
+ * Snooker update of ter Braak & Vrugt (2008) — cited by the reference (README.md:57-59) but not implemented there;
+ * restated from the paper, same Philox stream layout as the CUDA path (csrc/philox.cuh):
+ *   generation-level choice: ctr = (0xFFFFFFFF, gen lo, 0xFFFF0000, gen hi), word 0 -> u < prob
+ *   per chain: call 0xFFFF0000 -> (w_z, w_z1, w_z2, w_accept); three distinct rows by successive removal;
+ *              call 0xFFFF0001 word 0 -> gamma_s = 1.2 + u when gamma_s == 0
+ *   x' = x + gamma_s e ((z1 - z2).e)/(e.e), e = x - z; accept with pi(x')/pi(x) |1 + gamma_s proj|^(d-1)
+ * ------------------------------------------------------------------------------------------- */
+int orc_is_snooker_gen(uint64_t seed, int64_t gen_abs, double prob)
+{
+    if (!(prob > 0.0)) return 0;
+    const uint32_t key[2] = { (uint32_t)seed, (uint32_t)(seed >> 32) };
+    const uint32_t ctr[4] = { 0xFFFFFFFFu, (uint32_t)gen_abs, 0xFFFF0000u, (uint32_t)((uint64_t)gen_abs >> 32) };
+    uint32_t w[4];
+    orc_philox4x32_10(ctr, key, w);
+    return orc_uniform(w[0]) < prob;
+}
+
+void orc_snooker_generation(const orc_opts* o, const orc_lik* lik, double* X, double* lp, const double* Z, int64_t Zld,
+                            int64_t M, int64_t gen_abs, double gamma_s, int tempered, double T, const orc_trace* tr)
+{
+    const int d = o->d, N = o->N;
+    const uint32_t key[2] = { (uint32_t)o->seed, (uint32_t)(o->seed >> 32) };
+    for (int ic = 0; ic < N; ++ic) {
+        uint32_t ctr[4] = { (uint32_t)(o->chain_offset + ic), (uint32_t)gen_abs, 0xFFFF0000u, (uint32_t)((uint64_t)gen_abs >> 32) };
+        uint32_t w[4];
+        orc_philox4x32_10(ctr, key, w);
+        uint32_t z = (uint32_t)(((uint64_t)w[0] * (uint64_t)M) >> 32);
+        uint32_t j1 = (uint32_t)(((uint64_t)w[1] * (uint64_t)(M - 1)) >> 32);
+        uint32_t z1 = j1 + (j1 >= z ? 1u : 0u);
+        uint32_t z2 = (uint32_t)(((uint64_t)w[2] * (uint64_t)(M - 2)) >> 32);
+        const uint32_t lo = z < z1 ? z : z1, hi = z < z1 ? z1 : z;
+        if (z2 >= lo) ++z2;
+        if (z2 >= hi) ++z2;
+        double gs = (double)(float)gamma_s;
+        if (gamma_s == 0.0) {
+            uint32_t w2[4];
+            ctr[2] = 0xFFFF0001u;
+            orc_philox4x32_10(ctr, key, w2);
+            gs = (double)(float)(1.2f + (float)orc_uniform(w2[0]));            /* the device forms 1.2f + u in FP32 */
+        }
+        double x[64], xp[64], ee = 0.0, num = 0.0;
+        for (int k = 0; k < d; ++k) {
+            x[k] = X[ic + (size_t)N * k];
+            const double e = x[k] - ZAT(Z, Zld, d, o->z_rowmajor, z, k);
+            ee += e * e;
+            num += (ZAT(Z, Zld, d, o->z_rowmajor, z1, k) - ZAT(Z, Zld, d, o->z_rowmajor, z2, k)) * e;
+        }
+        const double proj = ee > 0.0 ? gs * num / ee : 0.0;
+        for (int k = 0; k < d; ++k) xp[k] = x[k] + proj * (x[k] - ZAT(Z, Zld, d, o->z_rowmajor, z, k));
+        const double lpp = orc_logdensity(lik, xp);
+        const double geo = (d - 1) * log(fabs(1.0 + proj));
+        const double u = orc_uniform(w[3]);
+        const double Tm = tempered ? T : 1.0;
+        const int acc = ee > 0.0 && (Tm * log(u) < (lpp - lp[ic]) + Tm * geo);
+        if (tr) {
+            if (tr->r1) tr->r1[ic] = z1;
+            if (tr->r2) tr->r2[ic] = z2;
+            if (tr->u) tr->u[ic] = u;
+            if (tr->lp_prop) tr->lp_prop[ic] = lpp;
+            if (tr->accepted) tr->accepted[ic] = (uint8_t)acc;
+            if (tr->xprop) for (int k = 0; k < d; ++k) tr->xprop[(size_t)k * N + ic] = xp[k];
+        }
+        if (acc) {
+            for (int k = 0; k < d; ++k) X[ic + (size_t)N * k] = xp[k];
+            lp[ic] = lpp;
+        }
+    }
 }

@@ -40,7 +40,7 @@ void orc_draw_pair(uint32_t w_r1, uint32_t w_r2, uint32_t M, uint32_t* r1, uint3
 void orc_box_muller16(uint32_t w, double* z0, double* z1);
 
 /* ---- likelihood descriptors (the reference passes a closure: src/demcz.jl:189) ------------- */
-enum { ORC_LIK_MVNORMAL = 0, ORC_LIK_LINREG = 1 };
+enum { ORC_LIK_MVNORMAL = 0, ORC_LIK_LINREG = 1, ORC_LIK_LOGISTIC = 2 };   /* 2: extension, sum(y*eta - log(1+exp(eta))) */
 
 typedef struct {
     int kind;
@@ -133,6 +133,12 @@ int orc_run(const orc_opts* o, const orc_run_opts* r, const orc_lik* lik,
             double* Z, int64_t Zld, int64_t M0, const double* X0, const double* lp0,
             double* chain, double* log_obj, double* Xout, double* lpout, double* rhat_out,
             orc_run_info* info);
+
+/* Snooker update of ter Braak & Vrugt (2008) for every chain (one proposal per chain, all coordinates) — an extension:
+ * the reference cites the paper (README.md:57-59) and implements the parallel update only.  Trace layout as one block. */
+int orc_is_snooker_gen(uint64_t seed, int64_t gen_abs, double prob);
+void orc_snooker_generation(const orc_opts* o, const orc_lik* lik, double* X, double* lp, const double* Z, int64_t Zld,
+                            int64_t M, int64_t gen_abs, double gamma_s, int tempered, double T, const orc_trace* tr);
 
 /* Rhat_gelman, src/utils.jl:2-20.  chain: N x d x G col-major; out: d */
 void orc_rhat_gelman(const double* chain, int N, int G, int d, double* out);

@@ -216,8 +216,8 @@ def snooker_update(X, lp, Z, M, lik, gamma_s, seed, gen_abs, T=None, chain_offse
     z2 = z2 + (z2 >= hi)
     if gamma_s == 0:
         ctr[..., 2] = np.uint64(SNOOKER_CALL + 1)
-        gs = 1.2 + uniform(philox4x32_10(ctr, key)[:, 0])
-        gs = gs.astype(np.float32).astype(np.float64)          # the device forms 1.2f + u in FP32
+        # the device forms 1.2f + u in FP32 (u is exact in FP32)
+        gs = (np.float32(1.2) + uniform(philox4x32_10(ctr, key)[:, 0]).astype(np.float32)).astype(np.float64)
     else:
         gs = np.full(N, float(np.float32(gamma_s)))
     ph = (lambda r: r) if zcap is None else (lambda r: (r + zstart) % zcap)
@@ -363,7 +363,7 @@ class COracle:
             L = np.asfortranarray(lik.L, dtype=np.float64)
             keep += [mu, L]
             s.mu, s.L, s.c0 = _ptr(mu), _ptr(L), lik.c0
-        else:
+        else:                                   # kind 1 (linreg) and 2 (logistic) carry X, y
             keep += [lik.X, lik.y]
             s.n, s.X, s.y = lik.n, _ptr(lik.X), _ptr(lik.y)
         s._keep = keep
@@ -398,6 +398,29 @@ class COracle:
 
     def tempbaseline(self, ig, Ng, T0, TN):
         return self.lib.orc_tempbaseline(ig, Ng, T0, TN)
+
+    def is_snooker_gen(self, seed, gen_abs, prob):
+        self.lib.orc_is_snooker_gen.argtypes = [C.c_uint64, C.c_int64, C.c_double]
+        return bool(self.lib.orc_is_snooker_gen(seed, gen_abs, prob))
+
+    def snooker_generation(self, X, lp, Z, M, lik, gamma_s, seed, gen_abs, T=None, chain_offset=0):
+        """orc_snooker_generation: returns (Xnew, lpnew, trace) like generation()."""
+        N, d = X.shape
+        Xf = np.asfortranarray(X, dtype=np.float64).copy(order="F")
+        lpf = np.array(lp, dtype=np.float64)
+        Zf = np.asfortranarray(Z, dtype=np.float64)
+        tr = dict(r1=np.zeros(N, np.uint32), r2=np.zeros(N, np.uint32), u=np.zeros(N), xprop=np.zeros((d, N)),
+                  lp_prop=np.zeros(N), accepted=np.zeros(N, np.uint8))
+        t = _Trace(*[_ptr(tr[k]) for k in ("r1", "r2", "u", "xprop", "lp_prop", "accepted")])
+        o = self.make_opts(N, 1, d, [list(range(d))], np.zeros(d), 0.0, seed, 0, chain_offset, 0, 0, 1)
+        s = self.make_lik(lik)
+        self.lib.orc_snooker_generation(C.byref(o), C.byref(s), _ptr(Xf), _ptr(lpf), _ptr(Zf), C.c_int64(Zf.shape[0]), C.c_int64(M),
+                                        C.c_int64(gen_abs), C.c_double(gamma_s), 0 if T is None else 1, C.c_double(1.0 if T is None else T),
+                                        C.byref(t))
+        tr["xprop"] = tr["xprop"].T
+        tr["accepted"] = tr["accepted"].astype(bool)
+        tr["r1"], tr["r2"] = tr["r1"].astype(np.int64), tr["r2"].astype(np.int64)
+        return Xf, lpf, tr
 
     # -- one generation (teacher-forced parity) -------------------------------------------------
     def generation(self, X, lp, Z, M, lik, blocks, eps_scale, gamma, seed, gen_abs, T=None, chain_offset=0,

@@ -90,3 +90,34 @@ def test_logistic_lik_matches_a_direct_evaluation():
     B = rng.normal(size=(4, 3))
     want = [np.sum(y * (X @ b) - np.log1p(np.exp(X @ b))) for b in B]
     np.testing.assert_allclose(orc.LogisticLik(X, y).logdensity(B), want, rtol=1e-12)
+
+
+def test_c_and_numpy_restatements_agree_on_snooker_and_logistic(coracle):
+    """The two independent restatements (C, numpy) of the round-2 extensions against each other: indices and uniforms
+    bit-exact, proposals / log-densities to FP64 rounding, decisions identical; generation-level choice identical."""
+    import numpy as np
+    from oracle import demcz_oracle as orc
+    rng = np.random.default_rng(2)
+    # logistic log-likelihood
+    X = np.asfortranarray(np.column_stack([np.ones(300), rng.normal(size=(300, 4))])); y = (rng.random(300) < 0.4).astype(float)
+    lik = orc.LogisticLik(X, y)
+    B = rng.normal(size=(6, 5)) * np.array([1, 1, 5, 0.1, 30])[None, :]          # incl. saturated eta
+    np.testing.assert_allclose(coracle.logdensity(lik, B), lik.logdensity(B), rtol=1e-12)
+    # snooker generation, MvNormal and logistic targets, fixed and random jump size, plain and tempered
+    d, N, M = 5, 64, 200
+    mv = orc.MvNormalLik(rng.normal(size=d), np.eye(d) + 0.3)
+    for lk, dd in ((mv, d), (lik, 5)):
+        Z = rng.normal(size=(M, dd)) * 0.3
+        Xs = rng.normal(size=(N, dd)) * 0.3
+        lp = lk.logdensity(Xs)
+        for gs, T in ((0.0, None), (1.7, None), (0.0, 0.5)):
+            a = orc.snooker_update(Xs, lp, Z, M, lk, gs, 99, 12345, T=T, chain_offset=7)
+            Xc, lpc, tr = coracle.snooker_generation(Xs, lp, Z, M, lk, gs, 99, 12345, T=T, chain_offset=7)
+            assert np.array_equal(tr["r1"], a["r1"]) and np.array_equal(tr["r2"], a["r2"]) and np.array_equal(tr["u"], a["u"])
+            np.testing.assert_allclose(tr["xprop"], a["xprop"], rtol=1e-12, atol=1e-14)
+            np.testing.assert_allclose(tr["lp_prop"], a["lp_prop"], rtol=1e-11)
+            assert np.array_equal(tr["accepted"], a["accepted"])
+            Xn = Xs.copy(); Xn[a["accepted"]] = a["xprop"][a["accepted"]]
+            np.testing.assert_allclose(Xc, Xn, rtol=1e-12, atol=1e-14)
+    for g in range(1, 200):
+        assert coracle.is_snooker_gen(31953150, g, 0.3) == orc.is_snooker_gen(31953150, g, 0.3)
