@@ -34,3 +34,29 @@ def test_numpy_oracle_follows_golden(name):
         np.testing.assert_allclose(X, chain[:, :, g - 1], rtol=1e-10, atol=1e-12, err_msg=f"generation {g}")
         np.testing.assert_allclose(lp, log_obj[:, g - 1], rtol=1e-9)
     np.testing.assert_allclose(orc.rhat_gelman(chain), GOLD[f"{name}.rhat"], rtol=1e-10)
+
+
+# ---- round-2 extensions: snooker update, logistic likelihood (tests/golden/extensions_golden.npz) ---------------------
+from tests.golden.make_golden_ext import cases, run_numpy  # noqa: E402
+
+GOLD_EXT = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "extensions_golden.npz"))
+
+
+@pytest.mark.parametrize("name", ["mvn", "logistic"])
+def test_snooker_golden_both_restatements(coracle, name):
+    c = cases()[name]
+    got = run_numpy(c)
+    for k, v in got.items():
+        if v.dtype.kind in "iub":
+            assert np.array_equal(v, GOLD_EXT[f"{name}.{k}"]), k
+        else:
+            np.testing.assert_allclose(v, GOLD_EXT[f"{name}.{k}"], rtol=1e-12, atol=1e-14, err_msg=k)
+    lp = c["lik"].logdensity(c["X"])
+    _, _, tr = coracle.snooker_generation(c["X"], lp, c["Z"], c["M"], c["lik"], c["gamma_s"], c["seed"], c["gen"], T=c["T"],
+                                          chain_offset=c["chain_offset"])
+    for k in ("r1", "r2", "accepted"):
+        assert np.array_equal(tr[k], GOLD_EXT[f"{name}.{k}"]), k
+    for k in ("u", "xprop", "lp_prop"):
+        np.testing.assert_allclose(tr[k], GOLD_EXT[f"{name}.{k}"], rtol=1e-11, atol=1e-13, err_msg=k)
+    if "B" in c:
+        np.testing.assert_allclose(coracle.logdensity(c["lik"], c["B"]), GOLD_EXT[f"{name}.logdensity"], rtol=1e-12)
